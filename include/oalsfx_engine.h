@@ -1,0 +1,119 @@
+/* oalsfx_engine.h -- C ABI of the batched B200 effects engine (the drop-in boundary).
+ *
+ * The reference has no FFI of its own; its only boundary is the C++ class oalsfxpp::Api
+ * (reference: src/oalsfxpp.h:760-922).  This ABI is what a binding for that class's hot path
+ * would call: one engine owns `num_streams` independent streams, each of which behaves exactly
+ * like one reference `Api` instance (same channel format, sampling rate and slot count for the
+ * whole engine).  include/oalsfxpp.h re-exports the reference's C++ class on top of it with
+ * num_streams = 1.
+ *
+ * Plain pointers and sizes only; no exceptions cross this boundary.  Every call returns
+ * OALSFX_OK (0) or a negative error code; oalsfx_last_error() gives the message.
+ * There is no CPU implementation behind this ABI: creation fails without a CUDA device.
+ */
+#ifndef OALSFX_ENGINE_H
+#define OALSFX_ENGINE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct oalsfx_engine oalsfx_engine;
+
+enum {
+	OALSFX_OK = 0,
+	OALSFX_ERR_ARGUMENT = -1,   /* bad index / pointer / size */
+	OALSFX_ERR_FORMAT = -2,     /* invalid channel format        (reference: oalsfxpp.cpp:2855-2861) */
+	OALSFX_ERR_RATE = -3,       /* sampling rate out of range    (reference: oalsfxpp.cpp:2863-2868) */
+	OALSFX_ERR_EFFECTS = -4,    /* effect count out of range     (reference: oalsfxpp.cpp:2870-2875) */
+	OALSFX_ERR_DEVICE = -5,     /* CUDA failure / no device */
+	OALSFX_ERR_MEMORY = -6
+};
+
+/* Sample buffer layouts for oalsfx_engine_mix.  F = frames of the call, C = channels. */
+enum {
+	OALSFX_LAYOUT_STREAM_MAJOR = 0, /* [stream][frame][channel]: every stream's buffer is exactly the
+	                                   interleaved buffer Api::mix takes (reference: oalsfxpp.h:872-875) */
+	OALSFX_LAYOUT_TILED = 1         /* [tile = stream/32][frame][channel][lane = stream%32]: engine-native,
+	                                   fully coalesced; the stream count is padded to a multiple of 32 */
+};
+
+enum { OALSFX_SPACE_HOST = 0, OALSFX_SPACE_DEVICE = 1 };
+
+typedef struct oalsfx_engine_desc {
+	int32_t device;         /* CUDA device ordinal */
+	int32_t num_streams;    /* >= 1 */
+	int32_t channel_format; /* oalsfxpp::ChannelFormat value (1 mono .. 7 seven_point_one) */
+	int32_t sampling_rate;  /* >= 8000 */
+	int32_t effect_count;   /* 1..4 slots per stream */
+} oalsfx_engine_desc;
+
+/* Replaces Api::initialize (reference: oalsfxpp.cpp:3480-3504, 2846-2905). */
+int oalsfx_engine_create(const oalsfx_engine_desc* desc, oalsfx_engine** out);
+
+/* Replaces Api::uninitialize / ~Api (reference: oalsfxpp.cpp:3831-3834). */
+void oalsfx_engine_destroy(oalsfx_engine* e);
+
+/* Replaces EffectSlot::set_effect as reached from Api::apply_changes (reference:
+ * oalsfxpp.cpp:2688-2709, 3748-3756) for streams [first_stream, first_stream + n_streams).
+ * `props` points at the bytes of an oalsfxpp::EffectProps (108 bytes; ignored for the null
+ * effect); they are normalized (clamped) like Effect::normalize does.  A change of effect TYPE
+ * resets that slot's state (delay lines, filter history), a change of properties keeps it.  The
+ * new coefficients take effect at the top of the next mixed block (reference: oalsfxpp.cpp:3000). */
+int oalsfx_engine_set_effect(oalsfx_engine* e, int first_stream, int n_streams, int slot,
+	int effect_type, const void* props, size_t props_bytes);
+
+/* Replaces the send half of Api::apply_changes (reference: oalsfxpp.cpp:3760-3780, 3348-3395).
+ * direct = {gain, gain_hf, gain_lf}; aux = effect_count such triples (slot order). */
+int oalsfx_engine_set_sends(oalsfx_engine* e, int first_stream, int n_streams,
+	const float* direct, const float* aux);
+
+/* Replaces Api::mix for all streams at once (reference: oalsfxpp.cpp:3785-3829, 2984-3037).
+ * `frames` per stream; internally cut into blocks of <= 2048 frames exactly like the reference.
+ * src/dst hold num_streams*frames*C floats (TILED: stream count rounded up to 32) in `space`;
+ * dst is overwritten, not clipped.  Device buffers must not overlap.  With host buffers the call
+ * stages through device memory and returns after the results are back; with device buffers the
+ * work is enqueued on `cuda_stream` (a cudaStream_t, may be NULL) and the call returns at once. */
+int oalsfx_engine_mix(oalsfx_engine* e, int frames, const float* src, float* dst,
+	int layout, int space, void* cuda_stream);
+
+/* Optional all-streams output bus: bus[frame][channel] (device, frames*C floats) = sum over this
+ * engine's streams of a STREAM_MAJOR/TILED device buffer `dst` produced by oalsfx_engine_mix.
+ * No reference counterpart; the cross-GPU sum is one all-reduce of `bus`. */
+int oalsfx_engine_reduce_bus(oalsfx_engine* e, int frames, const float* dst, int layout,
+	float* bus, void* cuda_stream);
+
+/* Integer state of one stream's slot, for bit-exact checks: out[0]=ring write offset,
+ * out[1]=reverb fade_count, out[2]=reverb mod index, out[3]=ring-mod phase index.
+ * Unused entries are 0.  Synchronizes the device. */
+int oalsfx_engine_debug_state(oalsfx_engine* e, int stream, int slot, int32_t out[4]);
+
+/* How many of the engine's kernels have been launched so far (bench.py's gpu_launches). */
+long long oalsfx_engine_launch_count(const oalsfx_engine* e);
+
+/* Bytes of device memory the engine currently holds. */
+long long oalsfx_engine_device_bytes(const oalsfx_engine* e);
+
+/* Message for the last failed call on this engine (or on creation when e == NULL). */
+const char* oalsfx_last_error(const oalsfx_engine* e);
+
+/* Property helpers for bindings (reference: Effect::set_type_and_defaults / Effect::normalize,
+ * oalsfxpp.cpp:1782-1833; ReverbPresets, oalsfxpp.cpp:1938-2191).  `props` = 108-byte EffectProps. */
+int oalsfx_effect_defaults(int effect_type, void* props, size_t props_bytes);
+int oalsfx_effect_normalize(int effect_type, void* props, size_t props_bytes);
+/* group/name as in the header, e.g. ("Default", "forest"); index-based enumeration via
+ * oalsfx_reverb_preset_name(i) which returns "Group::name" or NULL past the end. */
+int oalsfx_reverb_preset(const char* group, const char* name, void* props, size_t props_bytes);
+const char* oalsfx_reverb_preset_name(int index);
+
+/* Library build identification, e.g. "oalsfx_b200 sm_100a cuda". */
+const char* oalsfx_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* OALSFX_ENGINE_H */

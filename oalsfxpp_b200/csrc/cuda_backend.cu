@@ -1,0 +1,229 @@
+// cuda_backend.cu -- the one Backend the product links: CUDA runtime + the sm_100a kernels.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (no FMA contraction: parity
+// with the CPU reference needs separate FMUL/FADD), IEEE div/sqrt and
+// no flush-to-zero (nvcc defaults; -use_fast_math must never be passed).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "backend.h"
+#include "kernel_table.h"
+
+namespace oalsfx {
+namespace {
+
+__global__ void zero_lanes_kernel(uint32_t* base, long long tile_stride, int words, const TileRef* tiles)
+{
+	const TileRef t = tiles[blockIdx.y];
+	const int lane = threadIdx.x % kLanes;
+	if (!((t.mask >> lane) & 1U)) {
+		return;
+	}
+	const int warps_per_block = blockDim.x / kLanes;
+	uint32_t* p = base + static_cast<long long>(t.tile) * tile_stride + lane;
+	for (int w = blockIdx.x * warps_per_block + threadIdx.x / kLanes; w < words; w += gridDim.x * warps_per_block) {
+		p[static_cast<long long>(w) * kLanes] = 0U;
+	}
+}
+
+// One block per (frame, channel) pair; threads stride over the streams in a fixed pattern and the
+// partial sums are combined by a fixed shared-memory tree, so the result is deterministic.
+__global__ void reduce_bus_kernel(const float* data, long long ts, long long ls, long long fs, long long cs,
+	int num_streams, int channels, float* bus)
+{
+	__shared__ float partial[256];
+	const int frame = blockIdx.x / channels;
+	const int chan = blockIdx.x % channels;
+	float sum = 0.0F;
+	for (int s = threadIdx.x; s < num_streams; s += blockDim.x) {
+		sum += data[(s / kLanes) * ts + (s % kLanes) * ls + frame * fs + chan * cs];
+	}
+	partial[threadIdx.x] = sum;
+	__syncthreads();
+	for (int stride = blockDim.x / 2; stride > 0; stride /= 2) {
+		if (threadIdx.x < stride) {
+			partial[threadIdx.x] += partial[threadIdx.x + stride];
+		}
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) {
+		bus[blockIdx.x] = partial[0];
+	}
+}
+
+class CudaBackend final : public Backend {
+public:
+	explicit CudaBackend(int device) : device_(device) {}
+
+	const char* name() const override { return "cuda"; }
+
+	bool check(cudaError_t err, const char* what)
+	{
+		if (err == cudaSuccess) {
+			return true;
+		}
+		error_ = std::string(what) + ": " + cudaGetErrorString(err);
+		return false;
+	}
+
+	bool bind() { return check(cudaSetDevice(device_), "cudaSetDevice"); }
+
+	void* alloc(size_t bytes) override
+	{
+		if (!bind()) {
+			return nullptr;
+		}
+		void* p = nullptr;
+		if (!check(cudaMalloc(&p, bytes ? bytes : 1), "cudaMalloc")) {
+			return nullptr;
+		}
+		if (!check(cudaMemset(p, 0, bytes), "cudaMemset")) {
+			cudaFree(p);
+			return nullptr;
+		}
+		return p;
+	}
+
+	void release(void* p) override
+	{
+		if (p) {
+			cudaFree(p);
+		}
+	}
+
+	bool zero(void* p, size_t bytes, void* stream) override
+	{
+		return bind() && check(cudaMemsetAsync(p, 0, bytes, static_cast<cudaStream_t>(stream)), "cudaMemsetAsync");
+	}
+
+	bool upload(void* dst, const void* src, size_t bytes, void* stream) override
+	{
+		return bind() && check(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)),
+			"cudaMemcpyAsync(H2D)");
+	}
+
+	bool download(void* dst, const void* src, size_t bytes, void* stream) override
+	{
+		return bind() && check(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)),
+			"cudaMemcpyAsync(D2H)");
+	}
+
+	bool copy_2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width, size_t rows,
+		void* stream) override
+	{
+		return bind() && check(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width, rows, cudaMemcpyDeviceToDevice,
+			static_cast<cudaStream_t>(stream)), "cudaMemcpy2DAsync");
+	}
+
+	bool zero_lanes(uint32_t* base, long long tile_stride, int words, const TileRef* tiles, int n_tiles,
+		void* stream) override
+	{
+		if (!bind()) {
+			return false;
+		}
+		if (n_tiles <= 0 || words <= 0) {
+			return true;
+		}
+		cudaStream_t st = static_cast<cudaStream_t>(stream);
+		// Whole consecutive tiles: plain memset.
+		bool dense = true;
+		for (int i = 0; i < n_tiles && dense; ++i) {
+			dense = tiles[i].mask == 0xFFFFFFFFU && tiles[i].tile == tiles[0].tile + static_cast<uint32_t>(i);
+		}
+		if (dense && tile_stride == static_cast<long long>(words) * kLanes) {
+			return check(cudaMemsetAsync(base + static_cast<long long>(tiles[0].tile) * tile_stride, 0,
+				static_cast<size_t>(n_tiles) * static_cast<size_t>(tile_stride) * sizeof(uint32_t), st), "cudaMemsetAsync");
+		}
+		TileRef* dev_tiles = nullptr;
+		if (!check(cudaMalloc(&dev_tiles, static_cast<size_t>(n_tiles) * sizeof(TileRef)), "cudaMalloc")) {
+			return false;
+		}
+		bool ok = check(cudaMemcpyAsync(dev_tiles, tiles, static_cast<size_t>(n_tiles) * sizeof(TileRef),
+			cudaMemcpyHostToDevice, st), "cudaMemcpyAsync");
+		if (ok) {
+			for (int first = 0; first < n_tiles && ok; first += 65535) {
+				const int n = (n_tiles - first < 65535 ? n_tiles - first : 65535);
+				const int gx = (words + 7) / 8 < 64 ? (words + 7) / 8 : 64;
+				zero_lanes_kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n)), 256, 0, st>>>(
+					base, tile_stride, words, dev_tiles + first);
+				ok = check(cudaGetLastError(), "zero_lanes_kernel");
+			}
+		}
+		ok = check(cudaStreamSynchronize(st), "cudaStreamSynchronize") && ok;
+		cudaFree(dev_tiles);
+		return ok;
+	}
+
+	bool launch_mix(int kernel_id, const MixArgs& args, void* stream) override
+	{
+		if (!bind()) {
+			return false;
+		}
+		cudaStream_t st = static_cast<cudaStream_t>(stream);
+		constexpr int threads = 64;
+		const unsigned blocks = static_cast<unsigned>((static_cast<long long>(args.tile_count) * kLanes + threads - 1) / threads);
+		switch (kernel_id) {
+#define OALSFX_X(id, CT, SF, F0, F1, F2, F3) \
+		case id: mix_kernel<CT, SF, F0, F1, F2, F3><<<blocks, threads, 0, st>>>(args); break;
+			OALSFX_KERNEL_TABLE(OALSFX_X)
+#undef OALSFX_X
+		default:
+			error_ = "unknown kernel id";
+			return false;
+		}
+		return check(cudaGetLastError(), kernel_infos()[kernel_id].name);
+	}
+
+	bool reduce_bus(const float* data, long long ts, long long ls, long long fs, long long cs,
+		int num_streams, int frames, int channels, float* bus, void* stream) override
+	{
+		if (!bind()) {
+			return false;
+		}
+		reduce_bus_kernel<<<static_cast<unsigned>(frames * channels), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+			data, ts, ls, fs, cs, num_streams, channels, bus);
+		return check(cudaGetLastError(), "reduce_bus_kernel");
+	}
+
+	bool sync(void* stream) override
+	{
+		return bind() && check(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)), "cudaStreamSynchronize");
+	}
+
+	const std::string& error() const override { return error_; }
+
+private:
+	int device_;
+	std::string error_;
+};
+
+} // namespace
+
+Backend* make_backend(int device, std::string& error)
+{
+	int count = 0;
+	const cudaError_t err = cudaGetDeviceCount(&count);
+	if (err != cudaSuccess || count <= 0) {
+		error = std::string("No usable CUDA device (there is no CPU fallback): ") +
+			(err != cudaSuccess ? cudaGetErrorString(err) : "device count is 0");
+		return nullptr;
+	}
+	if (device < 0 || device >= count) {
+		error = "CUDA device ordinal out of range.";
+		return nullptr;
+	}
+	CudaBackend* be = new CudaBackend(device);
+	if (!be->bind()) {
+		error = be->error();
+		delete be;
+		return nullptr;
+	}
+	return be;
+}
+
+const char* backend_build_info() { return "oalsfx_b200 sm_100a cuda (fmad=false)"; }
+
+} // namespace oalsfx

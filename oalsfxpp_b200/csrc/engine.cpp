@@ -1,0 +1,842 @@
+// engine.cpp -- host logic of the batched engine behind include/oalsfx_engine.h.
+//
+// What it does (replacing the per-instance bookkeeping of the reference's Api::Impl,
+// oalsfxpp.cpp:2820-3432, for thousands of streams at once):
+//   * keeps per stream and slot an effect "class" (effect type + normalized properties) and per
+//     stream a send class; classes are de-duplicated, their coefficient blocks derived once on the
+//     host (derive.cpp);
+//   * owns the HBM arenas: per slot a lane-interleaved ring region sized by the largest effect type
+//     in that slot, per slot a state region, one send-filter state region;
+//   * at mix time groups streams by (slot classes, send class, pending-update bits) and launches one
+//     fused kernel per group and <= 2048-frame block, with the group's coefficient blocks as kernel
+//     arguments; signatures without a fused kernel run as a chain of single-effect passes that
+//     accumulate onto the bus in slot order (same summation order as the reference).
+//
+// No CUDA types here: device services come through backend.h.
+#include "oalsfx_engine.h"
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "backend.h"
+#include "derive.h"
+#include "kernel_table.h"
+
+using namespace oalsfx;
+
+namespace {
+
+std::string g_create_error;
+
+struct FxClass {
+	int type = kFxNull;
+	oalsfxpp::EffectProps props;
+	SlotCoef coef;          // device table pointers already patched in
+	bool used = false;      // scratch for compaction
+};
+
+struct SendClass {
+	SendSettings direct;
+	SendSettings aux[kMaxSlots];
+	SendCoef direct_coef;
+	SendCoef aux_coef[kMaxSlots];
+};
+
+struct GroupKey {
+	int fx[kMaxSlots];
+	int send;
+	uint32_t pending;
+	bool operator<(const GroupKey& o) const
+	{
+		return std::memcmp(this, &o, sizeof(GroupKey)) < 0;
+	}
+	bool operator==(const GroupKey& o) const { return std::memcmp(this, &o, sizeof(GroupKey)) == 0; }
+};
+
+struct Group {
+	GroupKey key;
+	bool identity = false;     // covers tiles 0..T-1 with all lanes
+	size_t tile_begin = 0;     // into the concatenated tile list
+	int tile_count = 0;
+};
+
+} // namespace
+
+struct oalsfx_engine {
+	oalsfx_engine_desc desc{};
+	DeviceLayout dev;
+	Backend* be = nullptr;
+	int streams = 0, tiles = 0, channels = 0, slots = 0;
+
+	// per-stream configuration (host)
+	std::vector<int> fx_class[kMaxSlots];
+	std::vector<int> send_class;
+	std::vector<uint8_t> pending;       // bit s: slot s has an un-consumed `update`
+
+	std::vector<FxClass> classes;
+	std::unordered_map<std::string, int> class_index;
+	std::vector<SendClass> send_classes;
+	std::map<std::string, void*> tables; // device lookup tables by content key
+
+	// device arenas
+	float* ring[kMaxSlots] = {};
+	int ring_cap[kMaxSlots] = {};        // words per lane
+	uint32_t* slot_state[kMaxSlots] = {};
+	uint32_t* send_state = nullptr;
+	TileRef* tile_list = nullptr;
+	size_t tile_list_cap = 0;
+	float* stage_in = nullptr;
+	float* stage_out = nullptr;
+	size_t stage_cap = 0;                // floats
+	long long device_bytes = 0;
+
+	std::vector<Group> groups;
+	bool groups_dirty = true;
+	long long launches = 0;
+	std::string error;
+
+	~oalsfx_engine()
+	{
+		if (!be) {
+			return;
+		}
+		be->sync(nullptr);
+		for (int s = 0; s < kMaxSlots; ++s) {
+			be->release(ring[s]);
+			be->release(slot_state[s]);
+		}
+		be->release(send_state);
+		be->release(tile_list);
+		be->release(stage_in);
+		be->release(stage_out);
+		for (auto& kv : tables) {
+			be->release(kv.second);
+		}
+		delete be;
+	}
+
+	int fail(int code, const std::string& msg)
+	{
+		error = msg;
+		return code;
+	}
+
+	void* dev_alloc(size_t bytes)
+	{
+		void* p = be->alloc(bytes);
+		if (p) {
+			device_bytes += static_cast<long long>(bytes);
+		}
+		return p;
+	}
+
+	// ---- classes --------------------------------------------------------------------------------
+	void* table_for(const std::string& key, const void* data, size_t bytes)
+	{
+		auto it = tables.find(key);
+		if (it != tables.end()) {
+			return it->second;
+		}
+		void* p = dev_alloc(bytes);
+		if (!p || !be->upload(p, data, bytes, nullptr) || !be->sync(nullptr)) {
+			return nullptr;
+		}
+		tables.emplace(key, p);
+		return p;
+	}
+
+	int class_for(int type, const oalsfxpp::EffectProps& props_in)
+	{
+		oalsfxpp::Effect fx;
+		std::memset(&fx, 0, sizeof(fx));
+		fx.type_ = static_cast<oalsfxpp::EffectType>(type);
+		if (type != kFxNull) {
+			fx.props_ = props_in;
+		}
+		fx.normalize();
+		// Key = type + the bytes of the property block that type uses.
+		size_t used = 0;
+		switch (type) {
+		case kFxChorus: used = sizeof(fx.props_.chorus_); break;
+		case kFxCompressor: used = sizeof(fx.props_.compressor_); break;
+		case kFxDedicatedDialog: case kFxDedicatedLfe: used = sizeof(fx.props_.dedicated_); break;
+		case kFxDistortion: used = sizeof(fx.props_.distortion_); break;
+		case kFxEcho: used = sizeof(fx.props_.echo_); break;
+		case kFxEqualizer: used = sizeof(fx.props_.equalizer_); break;
+		case kFxFlanger: used = sizeof(fx.props_.flanger_); break;
+		case kFxRingModulator: used = sizeof(fx.props_.ring_modulator_); break;
+		case kFxReverb: case kFxEaxReverb: used = offsetof(oalsfxpp::EffectProps::Reverb, decay_hf_limit_) + 1; break;
+		default: break;
+		}
+		std::string key(reinterpret_cast<const char*>(&type), sizeof(type));
+		key.append(reinterpret_cast<const char*>(&fx.props_), used);
+		auto it = class_index.find(key);
+		if (it != class_index.end()) {
+			return it->second;
+		}
+		FxClass c;
+		c.type = type;
+		c.props = fx.props_;
+		SlotTables t;
+		derive_slot(dev, desc.sampling_rate, type, fx.props_, c.coef, t);
+		if (!t.sin_delays.empty()) {
+			const ModDelayCoef& m = c.coef.u.mod_delay;
+			std::string tk = "sd";
+			tk.append(reinterpret_cast<const char*>(&m.lfo_range), 4);
+			tk.append(reinterpret_cast<const char*>(&m.lfo_scale), 4);
+			tk.append(reinterpret_cast<const char*>(&m.depth), 4);
+			tk.append(reinterpret_cast<const char*>(&m.delay), 4);
+			void* p = table_for(tk, t.sin_delays.data(), t.sin_delays.size() * sizeof(int32_t));
+			if (!p) {
+				return -1;
+			}
+			c.coef.u.mod_delay.sin_delays = static_cast<const int32_t*>(p);
+		}
+		if (!t.mod_sinus.empty()) {
+			std::string tk = "ms";
+			tk.append(reinterpret_cast<const char*>(&c.coef.u.reverb.mod_range), 4);
+			void* p = table_for(tk, t.mod_sinus.data(), t.mod_sinus.size() * sizeof(float));
+			if (!p) {
+				return -1;
+			}
+			c.coef.u.reverb.mod_sinus = static_cast<const float*>(p);
+		}
+		classes.push_back(c);
+		const int id = static_cast<int>(classes.size()) - 1;
+		class_index.emplace(key, id);
+		return id;
+	}
+
+	// Drop classes no stream refers to any more (cfg2-style per-block parameter changes would
+	// otherwise grow the table without bound).  Class 0 (null) always stays.
+	void compact_classes()
+	{
+		for (auto& c : classes) {
+			c.used = false;
+		}
+		classes[0].used = true;
+		for (int s = 0; s < kMaxSlots; ++s) {
+			for (int id : fx_class[s]) {
+				classes[static_cast<size_t>(id)].used = true;
+			}
+		}
+		std::vector<int> remap(classes.size(), -1);
+		std::vector<FxClass> kept;
+		for (size_t i = 0; i < classes.size(); ++i) {
+			if (classes[i].used) {
+				remap[i] = static_cast<int>(kept.size());
+				kept.push_back(classes[i]);
+			}
+		}
+		for (int s = 0; s < kMaxSlots; ++s) {
+			for (int& id : fx_class[s]) {
+				id = remap[static_cast<size_t>(id)];
+			}
+		}
+		for (auto it = class_index.begin(); it != class_index.end();) {
+			const int to = remap[static_cast<size_t>(it->second)];
+			if (to < 0) {
+				it = class_index.erase(it);
+			} else {
+				it->second = to;
+				++it;
+			}
+		}
+		classes.swap(kept);
+	}
+
+	int send_class_for(const SendSettings& direct, const SendSettings* aux)
+	{
+		for (size_t i = 0; i < send_classes.size(); ++i) {
+			const SendClass& sc = send_classes[i];
+			if (std::memcmp(&sc.direct, &direct, sizeof(direct)) == 0 &&
+				std::memcmp(sc.aux, aux, sizeof(SendSettings) * static_cast<size_t>(slots)) == 0) {
+				return static_cast<int>(i);
+			}
+		}
+		SendClass sc;
+		std::memset(&sc, 0, sizeof(sc));
+		sc.direct = direct;
+		for (int i = 0; i < slots; ++i) {
+			sc.aux[i] = aux[i];
+		}
+		derive_sends(dev, desc.sampling_rate, slots, sc.direct, sc.aux, sc.direct_coef, sc.aux_coef);
+		send_classes.push_back(sc);
+		return static_cast<int>(send_classes.size()) - 1;
+	}
+
+	// ---- arenas -------------------------------------------------------------------------------------
+	bool ensure_ring(int slot, int words)
+	{
+		if (words <= ring_cap[slot]) {
+			return true;
+		}
+		const size_t new_tile_bytes = static_cast<size_t>(words) * kLanes * sizeof(float);
+		float* fresh = static_cast<float*>(dev_alloc(new_tile_bytes * static_cast<size_t>(tiles)));
+		if (!fresh) {
+			return false;
+		}
+		if (ring[slot]) {
+			const size_t old_tile_bytes = static_cast<size_t>(ring_cap[slot]) * kLanes * sizeof(float);
+			if (!be->copy_2d(fresh, new_tile_bytes, ring[slot], old_tile_bytes, old_tile_bytes,
+					static_cast<size_t>(tiles), nullptr) || !be->sync(nullptr)) {
+				return false;
+			}
+			device_bytes -= static_cast<long long>(old_tile_bytes) * tiles;
+			be->release(ring[slot]);
+		}
+		ring[slot] = fresh;
+		ring_cap[slot] = words;
+		return true;
+	}
+
+	// (tile, mask) list of a stream range
+	static void tiles_of_range(int first, int n, std::vector<TileRef>& out)
+	{
+		out.clear();
+		const int last = first + n - 1;
+		for (int t = first / kLanes; t <= last / kLanes; ++t) {
+			const int lo = std::max(first, t * kLanes) - t * kLanes;
+			const int hi = std::min(last, t * kLanes + kLanes - 1) - t * kLanes;
+			const uint32_t mask = (hi - lo == 31 ? 0xFFFFFFFFU : ((1U << (hi - lo + 1)) - 1U) << lo);
+			out.push_back(TileRef{static_cast<uint32_t>(t), mask});
+		}
+	}
+
+	// ---- grouping -----------------------------------------------------------------------------------
+	GroupKey key_of(int s) const
+	{
+		GroupKey k;
+		std::memset(&k, 0, sizeof(k));
+		for (int i = 0; i < kMaxSlots; ++i) {
+			k.fx[i] = fx_class[i][static_cast<size_t>(s)];
+		}
+		k.send = send_class[static_cast<size_t>(s)];
+		k.pending = pending[static_cast<size_t>(s)];
+		return k;
+	}
+
+	bool rebuild_groups()
+	{
+		if (classes.size() > 256) {
+			compact_classes();
+		}
+		groups.clear();
+		const GroupKey k0 = key_of(0);
+		bool uniform = true;
+		for (int s = 1; s < streams && uniform; ++s) {
+			uniform = key_of(s) == k0;
+		}
+		if (uniform) {
+			Group g;
+			g.key = k0;
+			g.identity = true;
+			g.tile_count = tiles;
+			groups.push_back(g);
+			groups_dirty = false;
+			return true;
+		}
+		std::map<GroupKey, std::vector<TileRef>> by_key;
+		for (int s = 0; s < streams; ++s) {
+			std::vector<TileRef>& v = by_key[key_of(s)];
+			const uint32_t tile = static_cast<uint32_t>(s / kLanes);
+			if (v.empty() || v.back().tile != tile) {
+				v.push_back(TileRef{tile, 0});
+			}
+			v.back().mask |= 1U << (s % kLanes);
+		}
+		std::vector<TileRef> all;
+		for (auto& kv : by_key) {
+			Group g;
+			g.key = kv.first;
+			g.tile_begin = all.size();
+			g.tile_count = static_cast<int>(kv.second.size());
+			all.insert(all.end(), kv.second.begin(), kv.second.end());
+			groups.push_back(g);
+		}
+		if (all.size() > tile_list_cap) {
+			be->sync(nullptr);
+			be->release(tile_list);
+			tile_list_cap = all.size() * 2;
+			tile_list = static_cast<TileRef*>(dev_alloc(tile_list_cap * sizeof(TileRef)));
+			if (!tile_list) {
+				return false;
+			}
+		}
+		if (!be->upload(tile_list, all.data(), all.size() * sizeof(TileRef), nullptr) || !be->sync(nullptr)) {
+			return false;
+		}
+		groups_dirty = false;
+		return true;
+	}
+
+	// ---- launching ----------------------------------------------------------------------------------
+	void fill_common(MixArgs& a, const Group& g, int frames, const float* src, float* dst, int layout,
+		long long frames_total, long long frame0) const
+	{
+		std::memset(&a, 0, sizeof(a));
+		a.frames = frames;
+		a.channels = channels;
+		a.num_streams = streams;
+		if (layout == OALSFX_LAYOUT_TILED) {
+			a.io_ts = frames_total * channels * kLanes;
+			a.io_ls = 1;
+			a.io_fs = static_cast<long long>(channels) * kLanes;
+			a.io_cs = kLanes;
+		} else {
+			a.io_ts = frames_total * channels * kLanes;
+			a.io_ls = frames_total * channels;
+			a.io_fs = channels;
+			a.io_cs = 1;
+		}
+		a.src = src + frame0 * a.io_fs;
+		a.dst = dst + frame0 * a.io_fs;
+		a.tiles = g.identity ? nullptr : tile_list + g.tile_begin;
+		a.tile_count = g.tile_count;
+		a.send_state = send_state;
+		const SendClass& sc = send_classes[static_cast<size_t>(g.key.send)];
+		a.direct = sc.direct_coef;
+	}
+
+	void fill_slot(MixArgs& a, const Group& g, int pos, int slot, bool first_block) const
+	{
+		const FxClass& fc = classes[static_cast<size_t>(g.key.fx[slot])];
+		const SendClass& sc = send_classes[static_cast<size_t>(g.key.send)];
+		a.slot[pos] = fc.coef;
+		a.aux[pos] = sc.aux_coef[slot];
+		a.aux_index[pos] = slot;
+		a.ring[pos] = ring[slot];
+		a.ring_tile_stride[pos] = static_cast<long long>(ring_cap[slot]) * kLanes;
+		a.slot_state[pos] = slot_state[slot];
+		if (first_block && ((g.key.pending >> slot) & 1U)) {
+			a.update_mask |= 1U << pos;
+		}
+	}
+
+	bool launch_group(const Group& g, int frames, const float* src, float* dst, int layout,
+		long long frames_total, long long frame0, bool first_block, void* stream)
+	{
+		const SendClass& sc = send_classes[static_cast<size_t>(g.key.send)];
+		int kinds[kMaxSlots];
+		bool any_filter = sc.direct_coef.filter_type != 0;
+		for (int s = 0; s < kMaxSlots; ++s) {
+			const int type = classes[static_cast<size_t>(g.key.fx[s])].type;
+			kinds[s] = kind_of_type(type);
+			if (kinds[s] != kKindNull && sc.aux_coef[s].filter_type != 0) {
+				any_filter = true;
+			}
+		}
+		// A fused single-pass kernel for this signature?
+		const KernelInfo* infos = kernel_infos();
+		for (int k = 0; k < kKernelCount; ++k) {
+			const KernelInfo& ki = infos[k];
+			if (ki.ct != channels || ki.sf || any_filter || frames < 2) {
+				continue;
+			}
+			if (std::memcmp(ki.kind, kinds, sizeof(kinds)) != 0) {
+				continue;
+			}
+			MixArgs a;
+			fill_common(a, g, frames, src, dst, layout, frames_total, frame0);
+			a.with_dry = 1;
+			for (int s = 0; s < kMaxSlots; ++s) {
+				if (kinds[s] != kKindNull) {
+					fill_slot(a, g, s, s, first_block);
+				}
+			}
+			++launches;
+			return be->launch_mix(ki.id, a, stream);
+		}
+		// Chain of single-effect passes: the dry pass carries the first non-null slot.
+		static const int gen_for_kind[] = {kGenDry, kGenModDelay, kGenCompressor, kGenDedicated, kGenDistortion,
+			kGenEcho, kGenEqualizer, kGenRingMod, kGenReverb};
+		bool first = true;
+		for (int s = 0; s < kMaxSlots; ++s) {
+			if (kinds[s] == kKindNull) {
+				continue;
+			}
+			MixArgs a;
+			fill_common(a, g, frames, src, dst, layout, frames_total, frame0);
+			a.with_dry = first ? 1 : 0;
+			a.accumulate = first ? 0 : 1;
+			fill_slot(a, g, 0, s, first_block);
+			++launches;
+			if (!be->launch_mix(gen_for_kind[kinds[s]], a, stream)) {
+				return false;
+			}
+			first = false;
+		}
+		if (first) { // no effect at all: dry only
+			MixArgs a;
+			fill_common(a, g, frames, src, dst, layout, frames_total, frame0);
+			a.with_dry = 1;
+			++launches;
+			return be->launch_mix(kGenDry, a, stream);
+		}
+		return true;
+	}
+};
+
+// =================================================================================================
+extern "C" {
+
+int oalsfx_engine_create(const oalsfx_engine_desc* desc, oalsfx_engine** out)
+{
+	if (!desc || !out) {
+		g_create_error = "Null argument.";
+		return OALSFX_ERR_ARGUMENT;
+	}
+	*out = nullptr;
+	DeviceLayout dev;
+	// Same checks, same order and same messages as Api::Impl::initialize (oalsfxpp.cpp:2853-2875).
+	if (!make_device_layout(desc->channel_format, dev)) {
+		g_create_error = "Invalid channel format.";
+		return OALSFX_ERR_FORMAT;
+	}
+	if (desc->sampling_rate < 8000) {
+		g_create_error = "Sampling rate is out of range.";
+		return OALSFX_ERR_RATE;
+	}
+	if (desc->effect_count <= 0 || desc->effect_count > kMaxSlots) {
+		g_create_error = "Effect count is out of range.";
+		return OALSFX_ERR_EFFECTS;
+	}
+	if (desc->num_streams < 1) {
+		g_create_error = "Stream count is out of range.";
+		return OALSFX_ERR_ARGUMENT;
+	}
+	oalsfx_engine* e = new (std::nothrow) oalsfx_engine;
+	if (!e) {
+		g_create_error = "Failed to allocate the engine.";
+		return OALSFX_ERR_MEMORY;
+	}
+	e->desc = *desc;
+	e->dev = dev;
+	e->streams = desc->num_streams;
+	e->tiles = (desc->num_streams + kLanes - 1) / kLanes;
+	e->channels = dev.channels;
+	e->slots = desc->effect_count;
+	e->be = make_backend(desc->device, g_create_error);
+	if (!e->be) {
+		delete e;
+		return OALSFX_ERR_DEVICE;
+	}
+	const size_t slot_bytes = static_cast<size_t>(e->tiles) * kSlotStateWords * kLanes * sizeof(uint32_t);
+	for (int s = 0; s < e->slots; ++s) {
+		e->slot_state[s] = static_cast<uint32_t*>(e->dev_alloc(slot_bytes));
+		if (!e->slot_state[s]) {
+			g_create_error = "Device allocation failed: " + e->be->error();
+			delete e;
+			return OALSFX_ERR_MEMORY;
+		}
+	}
+	e->send_state = static_cast<uint32_t*>(
+		e->dev_alloc(static_cast<size_t>(e->tiles) * kSendStateWords * kLanes * sizeof(uint32_t)));
+	if (!e->send_state) {
+		g_create_error = "Device allocation failed: " + e->be->error();
+		delete e;
+		return OALSFX_ERR_MEMORY;
+	}
+	// Every slot starts as the null effect, every send at its defaults (oalsfxpp.cpp:2877-2902).
+	oalsfxpp::EffectProps none;
+	std::memset(&none, 0, sizeof(none));
+	e->class_for(kFxNull, none);
+	for (int s = 0; s < kMaxSlots; ++s) {
+		e->fx_class[s].assign(static_cast<size_t>(e->streams), 0);
+	}
+	SendSettings unit = {1.0F, 1.0F, 1.0F};
+	SendSettings aux[kMaxSlots] = {unit, unit, unit, unit};
+	e->send_class.assign(static_cast<size_t>(e->streams), e->send_class_for(unit, aux));
+	e->pending.assign(static_cast<size_t>(e->streams), 0);
+	*out = e;
+	return OALSFX_OK;
+}
+
+void oalsfx_engine_destroy(oalsfx_engine* e) { delete e; }
+
+int oalsfx_engine_set_effect(oalsfx_engine* e, int first_stream, int n_streams, int slot,
+	int effect_type, const void* props, size_t props_bytes)
+{
+	if (!e) {
+		return OALSFX_ERR_ARGUMENT;
+	}
+	if (first_stream < 0 || n_streams < 1 || first_stream + n_streams > e->streams) {
+		return e->fail(OALSFX_ERR_ARGUMENT, "Stream range is out of range.");
+	}
+	if (slot < 0 || slot >= e->slots) {
+		return e->fail(OALSFX_ERR_ARGUMENT, "Effect index is out of range.");
+	}
+	if (effect_type < 0 || effect_type >= kFxTypeCount) {
+		return e->fail(OALSFX_ERR_ARGUMENT, "Unknown effect type.");
+	}
+	oalsfxpp::EffectProps p;
+	std::memset(&p, 0, sizeof(p));
+	if (effect_type != kFxNull) {
+		if (!props || props_bytes != sizeof(oalsfxpp::EffectProps)) {
+			return e->fail(OALSFX_ERR_ARGUMENT, "props must be the bytes of an oalsfxpp::EffectProps.");
+		}
+		std::memcpy(&p, props, sizeof(p));
+	}
+	const int id = e->class_for(effect_type, p);
+	if (id < 0) {
+		return e->fail(OALSFX_ERR_MEMORY, "Lookup table upload failed: " + e->be->error());
+	}
+	if (!e->ensure_ring(slot, ring_words_for(effect_type, e->desc.sampling_rate))) {
+		return e->fail(OALSFX_ERR_MEMORY, "Delay-line arena allocation failed: " + e->be->error());
+	}
+	// A type change constructs a fresh effect state (oalsfxpp.cpp:2692-2698): zero the slot state and
+	// the rings of exactly those streams.
+	std::vector<TileRef> reset;
+	for (int s = first_stream; s < first_stream + n_streams; ++s) {
+		int& cur = e->fx_class[slot][static_cast<size_t>(s)];
+		if (e->classes[static_cast<size_t>(cur)].type != effect_type) {
+			const uint32_t tile = static_cast<uint32_t>(s / kLanes);
+			if (reset.empty() || reset.back().tile != tile) {
+				reset.push_back(TileRef{tile, 0});
+			}
+			reset.back().mask |= 1U << (s % kLanes);
+		}
+		cur = id;
+		e->pending[static_cast<size_t>(s)] |= static_cast<uint8_t>(1U << slot); // is_props_changed_ (oalsfxpp.cpp:2707)
+	}
+	if (!reset.empty()) {
+		const int n = static_cast<int>(reset.size());
+		if (!e->be->zero_lanes(e->slot_state[slot], static_cast<long long>(kSlotStateWords) * kLanes, kSlotStateWords,
+				reset.data(), n, nullptr)) {
+			return e->fail(OALSFX_ERR_DEVICE, e->be->error());
+		}
+		if (e->ring_cap[slot] > 0 && !e->be->zero_lanes(reinterpret_cast<uint32_t*>(e->ring[slot]),
+				static_cast<long long>(e->ring_cap[slot]) * kLanes, e->ring_cap[slot], reset.data(), n, nullptr)) {
+			return e->fail(OALSFX_ERR_DEVICE, e->be->error());
+		}
+	}
+	e->groups_dirty = true;
+	return OALSFX_OK;
+}
+
+int oalsfx_engine_set_sends(oalsfx_engine* e, int first_stream, int n_streams, const float* direct, const float* aux)
+{
+	if (!e) {
+		return OALSFX_ERR_ARGUMENT;
+	}
+	if (first_stream < 0 || n_streams < 1 || first_stream + n_streams > e->streams || !direct || !aux) {
+		return e->fail(OALSFX_ERR_ARGUMENT, "Bad stream range or null send properties.");
+	}
+	SendSettings d = {direct[0], direct[1], direct[2]};
+	SendSettings a[kMaxSlots];
+	std::memset(a, 0, sizeof(a));
+	for (int i = 0; i < e->slots; ++i) {
+		a[i] = SendSettings{aux[3 * i], aux[3 * i + 1], aux[3 * i + 2]};
+	}
+	const int id = e->send_class_for(d, a);
+	for (int s = first_stream; s < first_stream + n_streams; ++s) {
+		e->send_class[static_cast<size_t>(s)] = id;
+	}
+	e->groups_dirty = true;
+	return OALSFX_OK;
+}
+
+int oalsfx_engine_mix(oalsfx_engine* e, int frames, const float* src, float* dst, int layout, int space, void* cuda_stream)
+{
+	if (!e) {
+		return OALSFX_ERR_ARGUMENT;
+	}
+	if (frames == 0) {
+		return OALSFX_OK; // reference: oalsfxpp.cpp:3796-3799
+	}
+	if (frames < 0) {
+		return e->fail(OALSFX_ERR_ARGUMENT, "Negative frame count.");
+	}
+	if (!src) {
+		return e->fail(OALSFX_ERR_ARGUMENT, "No source samples.");
+	}
+	if (!dst) {
+		return e->fail(OALSFX_ERR_ARGUMENT, "No destination samples.");
+	}
+	if (layout != OALSFX_LAYOUT_STREAM_MAJOR && layout != OALSFX_LAYOUT_TILED) {
+		return e->fail(OALSFX_ERR_ARGUMENT, "Unknown layout.");
+	}
+	const long long padded = (layout == OALSFX_LAYOUT_TILED ? static_cast<long long>(e->tiles) * kLanes : e->streams);
+	const size_t count = static_cast<size_t>(padded) * static_cast<size_t>(frames) * static_cast<size_t>(e->channels);
+	const float* dsrc = src;
+	float* ddst = dst;
+	if (space == OALSFX_SPACE_HOST) {
+		if (count > e->stage_cap) {
+			e->be->sync(cuda_stream);
+			e->be->release(e->stage_in);
+			e->be->release(e->stage_out);
+			e->device_bytes -= static_cast<long long>(e->stage_cap) * 2 * sizeof(float);
+			e->stage_in = static_cast<float*>(e->dev_alloc(count * sizeof(float)));
+			e->stage_out = static_cast<float*>(e->dev_alloc(count * sizeof(float)));
+			e->stage_cap = count;
+			if (!e->stage_in || !e->stage_out) {
+				e->stage_cap = 0;
+				return e->fail(OALSFX_ERR_MEMORY, "Staging allocation failed: " + e->be->error());
+			}
+		}
+		if (!e->be->upload(e->stage_in, src, count * sizeof(float), cuda_stream)) {
+			return e->fail(OALSFX_ERR_DEVICE, e->be->error());
+		}
+		dsrc = e->stage_in;
+		ddst = e->stage_out;
+	} else if (space != OALSFX_SPACE_DEVICE) {
+		return e->fail(OALSFX_ERR_ARGUMENT, "Unknown pointer space.");
+	}
+
+	bool first_block = true;
+	for (int done = 0; done < frames;) {
+		const int todo = std::min(frames - done, kMaxBlockFrames); // oalsfxpp.cpp:3818-3826
+		if (e->groups_dirty && !e->rebuild_groups()) {
+			return e->fail(OALSFX_ERR_DEVICE, "Group table upload failed: " + e->be->error());
+		}
+		bool had_pending = false;
+		for (const Group& g : e->groups) {
+			had_pending = had_pending || g.key.pending != 0;
+			if (!e->launch_group(g, todo, dsrc, ddst, layout, frames, done, first_block, cuda_stream)) {
+				return e->fail(OALSFX_ERR_DEVICE, e->be->error());
+			}
+		}
+		if (had_pending) {
+			std::fill(e->pending.begin(), e->pending.end(), static_cast<uint8_t>(0));
+			e->groups_dirty = true;
+		}
+		first_block = false;
+		done += todo;
+	}
+
+	if (space == OALSFX_SPACE_HOST) {
+		if (!e->be->download(dst, e->stage_out, count * sizeof(float), cuda_stream) || !e->be->sync(cuda_stream)) {
+			return e->fail(OALSFX_ERR_DEVICE, e->be->error());
+		}
+	}
+	return OALSFX_OK;
+}
+
+int oalsfx_engine_reduce_bus(oalsfx_engine* e, int frames, const float* dst, int layout, float* bus, void* cuda_stream)
+{
+	if (!e || !dst || !bus || frames <= 0) {
+		return e ? e->fail(OALSFX_ERR_ARGUMENT, "Bad reduce_bus arguments.") : OALSFX_ERR_ARGUMENT;
+	}
+	long long ts, ls, fs, cs;
+	if (layout == OALSFX_LAYOUT_TILED) {
+		ts = static_cast<long long>(frames) * e->channels * kLanes;
+		ls = 1;
+		fs = static_cast<long long>(e->channels) * kLanes;
+		cs = kLanes;
+	} else {
+		ts = static_cast<long long>(frames) * e->channels * kLanes;
+		ls = static_cast<long long>(frames) * e->channels;
+		fs = e->channels;
+		cs = 1;
+	}
+	++e->launches;
+	if (!e->be->reduce_bus(dst, ts, ls, fs, cs, e->streams, frames, e->channels, bus, cuda_stream)) {
+		return e->fail(OALSFX_ERR_DEVICE, e->be->error());
+	}
+	return OALSFX_OK;
+}
+
+int oalsfx_engine_debug_state(oalsfx_engine* e, int stream, int slot, int32_t out[4])
+{
+	if (!e || !out || stream < 0 || stream >= e->streams || slot < 0 || slot >= e->slots) {
+		return e ? e->fail(OALSFX_ERR_ARGUMENT, "Bad debug_state arguments.") : OALSFX_ERR_ARGUMENT;
+	}
+	std::vector<uint32_t> words(static_cast<size_t>(kSlotStateWords) * kLanes);
+	const uint32_t* p = e->slot_state[slot] + static_cast<size_t>(stream / kLanes) * kSlotStateWords * kLanes;
+	if (!e->be->sync(nullptr) || !e->be->download(words.data(), p, words.size() * sizeof(uint32_t), nullptr) ||
+		!e->be->sync(nullptr)) {
+		return e->fail(OALSFX_ERR_DEVICE, e->be->error());
+	}
+	const int lane = stream % kLanes;
+	auto word = [&](size_t i) { return static_cast<int32_t>(words[i * kLanes + static_cast<size_t>(lane)]); };
+	out[0] = out[1] = out[2] = out[3] = 0;
+	const int type = e->classes[static_cast<size_t>(e->fx_class[slot][static_cast<size_t>(stream)])].type;
+	switch (kind_of_type(type)) {
+	case kKindModDelay: out[0] = word(offsetof(FxModDelay::State, offset) / 4); break;
+	case kKindEcho: out[0] = word(offsetof(FxEcho::State, offset) / 4); break;
+	case kKindRingMod: out[3] = word(offsetof(FxRingMod::State, index) / 4); break;
+	case kKindReverb:
+		out[0] = word(offsetof(FxReverb::State, offset) / 4);
+		out[1] = word(offsetof(FxReverb::State, fade_count) / 4);
+		out[2] = word(offsetof(FxReverb::State, mod_index) / 4);
+		break;
+	default: break;
+	}
+	return OALSFX_OK;
+}
+
+long long oalsfx_engine_launch_count(const oalsfx_engine* e) { return e ? e->launches : 0; }
+
+long long oalsfx_engine_device_bytes(const oalsfx_engine* e) { return e ? e->device_bytes : 0; }
+
+const char* oalsfx_last_error(const oalsfx_engine* e) { return e ? e->error.c_str() : g_create_error.c_str(); }
+
+const char* oalsfx_build_info(void) { return backend_build_info(); }
+
+int oalsfx_effect_defaults(int effect_type, void* props, size_t props_bytes)
+{
+	if (!props || props_bytes != sizeof(oalsfxpp::EffectProps) || effect_type < 0 || effect_type >= kFxTypeCount) {
+		return OALSFX_ERR_ARGUMENT;
+	}
+	oalsfxpp::Effect fx;
+	std::memset(&fx, 0, sizeof(fx));
+	fx.set_type_and_defaults(static_cast<oalsfxpp::EffectType>(effect_type));
+	std::memcpy(props, &fx.props_, sizeof(fx.props_));
+	return OALSFX_OK;
+}
+
+int oalsfx_effect_normalize(int effect_type, void* props, size_t props_bytes)
+{
+	if (!props || props_bytes != sizeof(oalsfxpp::EffectProps) || effect_type < 0 || effect_type >= kFxTypeCount) {
+		return OALSFX_ERR_ARGUMENT;
+	}
+	oalsfxpp::Effect fx;
+	fx.type_ = static_cast<oalsfxpp::EffectType>(effect_type);
+	std::memcpy(&fx.props_, props, sizeof(fx.props_));
+	fx.normalize();
+	std::memcpy(props, &fx.props_, sizeof(fx.props_));
+	return OALSFX_OK;
+}
+
+namespace {
+struct PresetRow { const char* full; const oalsfxpp::EffectProps::Reverb* value; };
+const PresetRow kPresets[] = {
+#define OALSFX_PRESET_GROUP_BEGIN(G)
+#define OALSFX_PRESET(G, N, ...) {#G "::" #N, &oalsfxpp::ReverbPresets::G::N},
+#define OALSFX_PRESET_GROUP_END(G)
+#include "oalsfxpp_presets.inc"
+#undef OALSFX_PRESET_GROUP_BEGIN
+#undef OALSFX_PRESET
+#undef OALSFX_PRESET_GROUP_END
+};
+constexpr int kPresetCount = static_cast<int>(sizeof(kPresets) / sizeof(kPresets[0]));
+} // namespace
+
+int oalsfx_reverb_preset(const char* group, const char* name, void* props, size_t props_bytes)
+{
+	if (!group || !name || !props || props_bytes != sizeof(oalsfxpp::EffectProps)) {
+		return OALSFX_ERR_ARGUMENT;
+	}
+	const std::string full = std::string(group) + "::" + name;
+	for (int i = 0; i < kPresetCount; ++i) {
+		if (full == kPresets[i].full) {
+			oalsfxpp::EffectProps p;
+			std::memset(&p, 0, sizeof(p));
+			p.reverb_ = *kPresets[i].value;
+			std::memcpy(props, &p, sizeof(p));
+			return OALSFX_OK;
+		}
+	}
+	return OALSFX_ERR_ARGUMENT;
+}
+
+const char* oalsfx_reverb_preset_name(int index)
+{
+	return (index >= 0 && index < kPresetCount) ? kPresets[index].full : nullptr;
+}
+
+} // extern "C"

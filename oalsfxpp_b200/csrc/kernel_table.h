@@ -1,0 +1,89 @@
+// kernel_table.h -- the list of mix_kernel instantiations.
+//
+// X(id, CT, SF, F0, F1, F2, F3):
+//   CT  compile-time channel count (0 = run-time, any layout)
+//   SF  send shelf filters compiled in (false = host guarantees none is active and frames >= 2)
+//   F*  effect processor per slot position
+//
+// "Gen*" entries process ONE effect in slot position 0 for any channel count; the engine chains
+// them (dry pass first, then one accumulate pass per remaining slot) for slot signatures that have
+// no fused entry.  The fused entries cover the BASELINE.json configurations in a single pass.
+#ifndef OALSFX_KERNEL_TABLE_H
+#define OALSFX_KERNEL_TABLE_H
+
+#include "mix.cuh"
+
+#define OALSFX_KERNEL_TABLE(X) \
+	X(kGenDry, 0, true, FxNull, FxNull, FxNull, FxNull) \
+	X(kGenModDelay, 0, true, FxModDelay, FxNull, FxNull, FxNull) \
+	X(kGenCompressor, 0, true, FxCompressor, FxNull, FxNull, FxNull) \
+	X(kGenDedicated, 0, true, FxDedicated, FxNull, FxNull, FxNull) \
+	X(kGenDistortion, 0, true, FxDistortion, FxNull, FxNull, FxNull) \
+	X(kGenEcho, 0, true, FxEcho, FxNull, FxNull, FxNull) \
+	X(kGenEqualizer, 0, true, FxEqualizer, FxNull, FxNull, FxNull) \
+	X(kGenRingMod, 0, true, FxRingMod, FxNull, FxNull, FxNull) \
+	X(kGenReverb, 0, true, FxReverb, FxNull, FxNull, FxNull) \
+	/* cfg2 / cfg4: equalizer + chorus + echo + (EAX) reverb, stereo */ \
+	X(kChainStereo, 2, false, FxEqualizer, FxModDelay, FxEcho, FxReverb) \
+	/* cfg3: flanger + ring modulator + distortion + compressor, mono */ \
+	X(kChain2Mono, 1, false, FxModDelay, FxRingMod, FxDistortion, FxCompressor) \
+	/* cfg1: one (EAX) reverb slot, mono */ \
+	X(kReverbMono, 1, false, FxReverb, FxNull, FxNull, FxNull) \
+	/* cfg0: one echo slot, stereo */ \
+	X(kEchoStereo, 2, false, FxEcho, FxNull, FxNull, FxNull)
+
+namespace oalsfx {
+
+enum KernelId : int {
+#define OALSFX_X(id, CT, SF, F0, F1, F2, F3) id,
+	OALSFX_KERNEL_TABLE(OALSFX_X)
+#undef OALSFX_X
+	kKernelCount
+};
+
+// Effect "kind" = which processor handles an FxType (chorus/flanger and reverb/EAX share one).
+enum FxKind : int { kKindNull, kKindModDelay, kKindCompressor, kKindDedicated, kKindDistortion, kKindEcho,
+	kKindEqualizer, kKindRingMod, kKindReverb };
+
+template <class F> struct KindOf;
+template <> struct KindOf<FxNull> { static constexpr int value = kKindNull; };
+template <> struct KindOf<FxModDelay> { static constexpr int value = kKindModDelay; };
+template <> struct KindOf<FxCompressor> { static constexpr int value = kKindCompressor; };
+template <> struct KindOf<FxDedicated> { static constexpr int value = kKindDedicated; };
+template <> struct KindOf<FxDistortion> { static constexpr int value = kKindDistortion; };
+template <> struct KindOf<FxEcho> { static constexpr int value = kKindEcho; };
+template <> struct KindOf<FxEqualizer> { static constexpr int value = kKindEqualizer; };
+template <> struct KindOf<FxRingMod> { static constexpr int value = kKindRingMod; };
+template <> struct KindOf<FxReverb> { static constexpr int value = kKindReverb; };
+
+inline int kind_of_type(int fx_type)
+{
+	switch (fx_type) {
+	case kFxChorus: case kFxFlanger: return kKindModDelay;
+	case kFxCompressor: return kKindCompressor;
+	case kFxDedicatedDialog: case kFxDedicatedLfe: return kKindDedicated;
+	case kFxDistortion: return kKindDistortion;
+	case kFxEcho: return kKindEcho;
+	case kFxEqualizer: return kKindEqualizer;
+	case kFxRingModulator: return kKindRingMod;
+	case kFxReverb: case kFxEaxReverb: return kKindReverb;
+	default: return kKindNull;
+	}
+}
+
+struct KernelInfo { int id; int ct; bool sf; int kind[4]; const char* name; };
+
+inline const KernelInfo* kernel_infos()
+{
+	static const KernelInfo infos[] = {
+#define OALSFX_X(id, CT, SF, F0, F1, F2, F3) \
+		{id, CT, SF, {KindOf<F0>::value, KindOf<F1>::value, KindOf<F2>::value, KindOf<F3>::value}, #id},
+		OALSFX_KERNEL_TABLE(OALSFX_X)
+#undef OALSFX_X
+	};
+	return infos;
+}
+
+} // namespace oalsfx
+
+#endif

@@ -1,0 +1,101 @@
+// TEST INFRASTRUCTURE ONLY -- a Backend (oalsfxpp_b200/csrc/backend.h) that runs the engine's
+// __host__ __device__ kernel bodies on the CPU, one (tile, lane) at a time.
+//
+// Purpose: let `pytest -m "not gpu"` exercise the engine's host logic (classes, grouping, arenas,
+// block chunking, multi-pass chaining, the Api shell) and the per-sample arithmetic against the
+// oracle in a container without a GPU.  It is built into tests/_build/liboalsfx_emu.so by
+// tests/emu/Makefile, is never part of the package and is not a fallback: liboalsfx_b200.so links
+// cuda_backend.cu only and refuses to create an engine without a CUDA device.
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "backend.h"
+#include "kernel_table.h"
+
+namespace oalsfx {
+namespace {
+
+class HostBackend final : public Backend {
+public:
+	const char* name() const override { return "host-emu"; }
+	void* alloc(size_t bytes) override { return std::calloc(bytes ? bytes : 1, 1); }
+	void release(void* p) override { std::free(p); }
+	bool zero(void* p, size_t bytes, void*) override { std::memset(p, 0, bytes); return true; }
+	bool upload(void* dst, const void* src, size_t bytes, void*) override { std::memcpy(dst, src, bytes); return true; }
+	bool download(void* dst, const void* src, size_t bytes, void*) override { std::memcpy(dst, src, bytes); return true; }
+	bool copy_2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width, size_t rows, void*) override
+	{
+		for (size_t r = 0; r < rows; ++r) {
+			std::memcpy(static_cast<char*>(dst) + r * dst_pitch, static_cast<const char*>(src) + r * src_pitch, width);
+		}
+		return true;
+	}
+	bool zero_lanes(uint32_t* base, long long tile_stride, int words, const TileRef* tiles, int n_tiles, void*) override
+	{
+		for (int i = 0; i < n_tiles; ++i) {
+			for (int lane = 0; lane < kLanes; ++lane) {
+				if (!((tiles[i].mask >> lane) & 1U)) {
+					continue;
+				}
+				uint32_t* p = base + static_cast<long long>(tiles[i].tile) * tile_stride + lane;
+				for (int w = 0; w < words; ++w) {
+					p[static_cast<long long>(w) * kLanes] = 0U;
+				}
+			}
+		}
+		return true;
+	}
+	bool launch_mix(int kernel_id, const MixArgs& a, void*) override
+	{
+		for (int w = 0; w < a.tile_count; ++w) {
+			int tile = w;
+			uint32_t mask = 0xFFFFFFFFU;
+			if (a.tiles) {
+				tile = static_cast<int>(a.tiles[w].tile);
+				mask = a.tiles[w].mask;
+			}
+			for (int lane = 0; lane < kLanes; ++lane) {
+				if (!((mask >> lane) & 1U) || tile * kLanes + lane >= a.num_streams) {
+					continue;
+				}
+				switch (kernel_id) {
+#define OALSFX_X(id, CT, SF, F0, F1, F2, F3) \
+				case id: mix_stream<CT, SF, F0, F1, F2, F3>(a, tile, lane); break;
+					OALSFX_KERNEL_TABLE(OALSFX_X)
+#undef OALSFX_X
+				default:
+					error_ = "unknown kernel id";
+					return false;
+				}
+			}
+		}
+		return true;
+	}
+	bool reduce_bus(const float* data, long long ts, long long ls, long long fs, long long cs,
+		int num_streams, int frames, int channels, float* bus, void*) override
+	{
+		for (int f = 0; f < frames; ++f) {
+			for (int c = 0; c < channels; ++c) {
+				double sum = 0.0;
+				for (int s = 0; s < num_streams; ++s) {
+					sum += data[(s / kLanes) * ts + (s % kLanes) * ls + f * fs + c * cs];
+				}
+				bus[f * channels + c] = static_cast<float>(sum);
+			}
+		}
+		return true;
+	}
+	bool sync(void*) override { return true; }
+	const std::string& error() const override { return error_; }
+
+private:
+	std::string error_;
+};
+
+} // namespace
+
+Backend* make_backend(int, std::string&) { return new HostBackend; }
+const char* backend_build_info() { return "oalsfx host-emu (tests only)"; }
+
+} // namespace oalsfx

@@ -1,0 +1,229 @@
+"""Shared test plumbing: builds/loads the CPU checkers and drives "scripts" through them.
+
+Checkers (all test infrastructure, see oracle/README.md):
+  * ``ref``    oracle/_ref/liboalsfx_ref.so      -- the unmodified reference behind a C shim
+  * ``oracle`` oracle/_build/liboalsfx_oracle.so -- the hand-written CPU restatement
+Both export the same ``orc_*`` ABI (oracle/ref_shim.cpp).
+
+Systems under test:
+  * ``emu``  tests/_build/liboalsfx_emu.so  -- engine host logic + kernel bodies on the CPU (no GPU)
+  * ``cuda`` oalsfxpp_b200/liboalsfx_b200.so -- the product
+Both export the C ABI of include/oalsfx_engine.h; the drop-in ``oalsfxpp::Api`` class of either is
+reached through the very same shim source the reference is wrapped with (oracle/ref_shim.cpp,
+compiled against include/oalsfxpp.h instead of the reference's header).
+
+A *script* is a list of ops replayed identically against a checker and a system under test:
+  ("type", slot, EffectType)            Api::set_effect_type
+  ("props", slot, EffectProps)          Api::set_effect_props
+  ("send", index, (gain, hf, lf))       Api::set_send_props   (index < 0: direct)
+  ("apply",)                            Api::apply_changes
+  ("mix", frames)                       Api::mix on the next `frames` frames of the input
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oalsfxpp_b200 import engine as _eng  # noqa: E402
+from oalsfxpp_b200.props import EffectProps, EffectType, channel_count  # noqa: E402
+
+REF_SRC = "/root/reference/src"
+SEED = 0x0A15F00D
+
+
+def _run(cmd, **kw):
+    subprocess.run(cmd, check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, **kw)
+
+
+def build_checkers():
+    _run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "all"])
+
+
+def build_emu():
+    _run(["make", "-s", "-C", os.path.join(ROOT, "tests", "emu")])
+
+
+def _bind_orc(lib):
+    vp, i32 = C.c_void_p, C.c_int
+    lib.orc_kind.restype = C.c_char_p
+    lib.orc_create.argtypes = [i32, i32, i32]
+    lib.orc_create.restype = vp
+    lib.orc_destroy.argtypes = [vp]
+    lib.orc_destroy.restype = None
+    lib.orc_channel_count.argtypes = [vp]
+    lib.orc_set_effect_type.argtypes = [vp, i32, i32]
+    lib.orc_set_effect_props.argtypes = [vp, i32, vp]
+    lib.orc_get_effect.argtypes = [vp, i32, C.POINTER(i32), vp]
+    lib.orc_get_deferred_effect.argtypes = [vp, i32, C.POINTER(i32), vp]
+    lib.orc_set_send_props.argtypes = [vp, i32, C.POINTER(C.c_float)]
+    lib.orc_apply.argtypes = [vp]
+    lib.orc_mix.argtypes = [vp, i32, vp, vp]
+    lib.orc_noise.argtypes = [C.c_uint32, C.c_uint32, i32, i32, i32, vp]
+    lib.orc_noise.restype = None
+    lib.orc_bench.argtypes = [i32, i32, i32, i32, C.POINTER(i32), i32, i32, i32, C.c_uint32, C.POINTER(C.c_double)]
+    lib.orc_bench.restype = C.c_double
+    return lib
+
+
+_CACHE = {}
+
+
+def ref_lib(fast=False):
+    """The compiled reference, or None when neither the mount nor a prebuilt .so is there."""
+    key = "ref_fast" if fast else "ref"
+    if key not in _CACHE:
+        path = os.path.join(ROOT, "oracle", "_ref", "liboalsfx_ref_fast.so" if fast else "liboalsfx_ref.so")
+        if not os.path.exists(path) and os.path.isdir(REF_SRC):
+            build_checkers()
+        _CACHE[key] = _bind_orc(C.CDLL(path)) if os.path.exists(path) else None
+    return _CACHE[key]
+
+
+def oracle_lib():
+    if "oracle" not in _CACHE:
+        path = os.path.join(ROOT, "oracle", "_build", "liboalsfx_oracle.so")
+        _run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+        _CACHE["oracle"] = _bind_orc(C.CDLL(path))
+    return _CACHE["oracle"]
+
+
+def checker_lib():
+    """Strongest checker available: the real reference, else the restatement."""
+    return ref_lib() or oracle_lib()
+
+
+def emu_lib():
+    if "emu" not in _CACHE:
+        build_emu()
+        _CACHE["emu"] = _eng.bind(C.CDLL(os.path.join(ROOT, "tests", "_build", "liboalsfx_emu.so")))
+    return _CACHE["emu"]
+
+
+def cuda_lib():
+    return _eng.load_library()
+
+
+def api_shim(kind):
+    """oracle/ref_shim.cpp compiled against include/oalsfxpp.h and linked to the emu / cuda library:
+    the drop-in proof for the C++ class."""
+    key = "shim_" + kind
+    if key not in _CACHE:
+        out_dir = os.path.join(ROOT, "tests", "_build")
+        os.makedirs(out_dir, exist_ok=True)
+        out = os.path.join(out_dir, f"libapi_shim_{kind}.so")
+        if kind == "emu":
+            emu_lib()
+            libdir, libname = out_dir, "oalsfx_emu"
+        else:
+            libdir, libname = os.path.join(ROOT, "oalsfxpp_b200"), "oalsfx_b200"
+        src = os.path.join(ROOT, "oracle", "ref_shim.cpp")
+        dep = os.path.join(libdir, f"lib{libname}.so")
+        if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(dep)):
+            _run(["g++", "-std=c++14", "-O2", "-fPIC", "-shared", "-pthread", "-I", os.path.join(ROOT, "include"),
+                  "-o", out, src, "-L", libdir, "-l" + libname, "-Wl,-rpath," + libdir])
+        _CACHE[key] = _bind_orc(C.CDLL(out))
+    return _CACHE[key]
+
+
+# ---- inputs --------------------------------------------------------------------------------------
+def _fmix32(h):
+    h = h.astype(np.uint32)
+    h ^= h >> np.uint32(16)
+    h = (h * np.uint32(0x85EBCA6B)).astype(np.uint32)
+    h ^= h >> np.uint32(13)
+    h = (h * np.uint32(0xC2B2AE35)).astype(np.uint32)
+    h ^= h >> np.uint32(16)
+    return h
+
+
+def noise(stream, channels, frames, first_frame=0, seed=SEED):
+    """SURVEY.md 8d synthetic white noise, [frames][channels] float32 in [-0.5, 0.5)."""
+    with np.errstate(over="ignore"):
+        n = (np.arange(first_frame, first_frame + frames, dtype=np.uint32)[:, None] * np.uint32(0xC2B2AE35))
+        c = (np.arange(channels, dtype=np.uint32)[None, :] * np.uint32(0x85EBCA6B))
+        s = np.uint32((stream * 0x9E3779B9) & 0xFFFFFFFF)
+        h = _fmix32(np.uint32(seed) ^ s ^ c ^ n)
+    return (((h >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 8388608.0)) - np.float32(1.0)) * np.float32(0.5)
+
+
+def sine(stream, channels, frames, rate):
+    f = 110.0 * 2.0 ** ((stream % 48) / 12.0)
+    t = np.arange(frames, dtype=np.float64)
+    x = (0.5 * np.sin(2.0 * np.pi * f * t / rate)).astype(np.float32)
+    return np.repeat(x[:, None], channels, axis=1).copy()
+
+
+def impulse(channels, frames):
+    x = np.zeros((frames, channels), dtype=np.float32)
+    x[0, :] = 0.5
+    return x
+
+
+def burst(stream, channels, frames, active):
+    x = noise(stream, channels, frames)
+    x[active:, :] = 0.0
+    return x
+
+
+# ---- script replay -------------------------------------------------------------------------------
+def run_script_orc(lib, channel_format, rate, effect_count, script, x):
+    """Replay `script` through an orc_* library (reference, restatement or Api shim).  x: [frames][C]."""
+    h = lib.orc_create(int(channel_format), rate, effect_count)
+    assert h, "orc_create failed"
+    try:
+        ch = channel_count(channel_format)
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        y = np.zeros_like(x)
+        pos = 0
+        for op in script:
+            if op[0] == "type":
+                assert lib.orc_set_effect_type(h, op[1], int(op[2]))
+            elif op[0] == "props":
+                assert lib.orc_set_effect_props(h, op[1], C.addressof(op[2]))
+            elif op[0] == "send":
+                g = (C.c_float * 3)(*op[2])
+                assert lib.orc_set_send_props(h, op[1], g)
+            elif op[0] == "apply":
+                assert lib.orc_apply(h)
+            elif op[0] == "mix":
+                n = op[1]
+                assert lib.orc_mix(h, n, x[pos:].ctypes.data, y[pos:].ctypes.data)
+                pos += n
+            else:
+                raise ValueError(op)
+        assert pos * ch == x.size, (pos, x.shape)
+        return y
+    finally:
+        lib.orc_destroy(h)
+
+
+def simple_script(slots, blocks, sends=None):
+    """Set the slot effects (type, props-or-None), optional sends, apply, then mix the blocks."""
+    script = []
+    for i, (etype, props) in enumerate(slots):
+        script.append(("type", i, etype))
+        if props is not None:
+            script.append(("props", i, props))
+    for index, triple in (sends or {}).items():
+        script.append(("send", index, triple))
+    script.append(("apply",))
+    # Aux send props written directly only take effect with the next refresh; a second apply makes the
+    # first mix see them in the reference as well (it flags the source as changed).
+    script.extend(("mix", n) for n in blocks)
+    return script
+
+
+def blocks_of(total, block):
+    out = [block] * (total // block)
+    if total % block:
+        out.append(total % block)
+    return out
+
+
+def max_abs_diff(a, b):
+    return float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64)))) if a.size else 0.0
