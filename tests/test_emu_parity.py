@@ -1,0 +1,135 @@
+"""CPU-only parity: the engine's host logic + the __host__ __device__ kernel bodies (compiled for the
+CPU into tests/_build/liboalsfx_emu.so, test infrastructure) against the CPU checker.  Bit-exact.
+
+These tests prove the algorithm restatement and all host-side logic without a GPU; the same cases
+run on the device in test_gpu_parity.py.
+"""
+import numpy as np
+import pytest
+
+import cases
+import harness as H
+import oalsfxpp_b200 as ox
+from oalsfxpp_b200 import ChannelFormat as F, EffectType as T
+
+CASES = list(cases.all_cases(H.emu_lib(), quick=True))
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_api_shell_matches_checker_bit_for_bit(case, checker):
+    name, fmt, rate, effect_count, script, x = case
+    expect = H.run_script_orc(checker, fmt, rate, effect_count, script, x)
+    got = H.run_script_orc(H.api_shim("emu"), fmt, rate, effect_count, script, x)
+    assert np.array_equal(expect.view(np.uint32), got.view(np.uint32)), H.max_abs_diff(expect, got)
+
+
+def _expected(checker, fmt, rate, slots, blocks, x):
+    script = H.simple_script(slots, blocks)
+    return H.run_script_orc(checker, fmt, rate, len(slots), script, x)
+
+
+@pytest.mark.parametrize("layout", [ox.LAYOUT_STREAM_MAJOR, ox.LAYOUT_TILED])
+def test_batched_engine_heterogeneous_streams(checker, layout):
+    """70 streams (ragged last tile), three different slot signatures and parameter sets interleaved
+    inside tiles; every stream must equal its own single-instance checker run."""
+    lib = H.emu_lib()
+    S, frames, block = 70, 2500, 1024
+    blocks = H.blocks_of(frames, block)
+    default = lambda t, **kw: ox.default_props(t, lib=lib, **kw)
+    configs = [
+        [(T.equalizer, None), (T.chorus, None), (T.echo, None), (T.eax_reverb, None)],
+        [(T.flanger, default(T.flanger, waveform_=0)), (T.ring_modulator, None), (T.distortion, None), (T.compressor, None)],
+        [(T.eax_reverb, ox.reverb_preset("Default", "forest", lib=lib)), (T.null, None), (T.echo, default(T.echo, delay_=0.05)), (T.null, None)],
+    ]
+    which = [(s * 7 + s // 5) % 3 for s in range(S)]
+    x = np.stack([H.noise(100 + s, 2, frames) for s in range(S)])
+    with ox.Engine(S, F.stereo, 48000, 4, lib=lib) as eng:
+        for s in range(S):
+            for slot, (t, p) in enumerate(configs[which[s]]):
+                eng.set_effect(slot, t, p, first_stream=s, n_streams=1)
+        y = np.empty_like(x)
+        pos = 0
+        for n in blocks:
+            xb = np.ascontiguousarray(x[:, pos:pos + n])
+            if layout == ox.LAYOUT_TILED:
+                pad = np.zeros((eng.padded_streams, n, 2), np.float32)
+                pad[:S] = xb
+                tiled = np.ascontiguousarray(pad.reshape(-1, 32, n, 2).transpose(0, 2, 3, 1))
+                out = eng.mix(tiled, layout=layout)
+                yb = out.transpose(0, 3, 1, 2).reshape(-1, n, 2)[:S]
+            else:
+                yb = eng.mix(xb)
+            y[:, pos:pos + n] = yb
+            pos += n
+    for s in range(S):
+        expect = _expected(checker, F.stereo, 48000, configs[which[s]], blocks, x[s])
+        assert np.array_equal(expect, y[s]), (s, which[s], H.max_abs_diff(expect, y[s]))
+
+
+def test_long_call_is_cut_into_2048_frame_blocks(checker):
+    """One 5000-frame call = blocks 2048, 2048, 904 (reference: oalsfxpp.cpp:3818-3826)."""
+    lib = H.emu_lib()
+    x = np.stack([H.noise(s, 1, 5000) for s in range(3)])
+    with ox.Engine(3, F.mono, 48000, 1, lib=lib) as eng:
+        eng.set_effect(0, T.eax_reverb)
+        y = eng.mix(x)
+    for s in range(3):
+        expect = _expected(checker, F.mono, 48000, [(T.eax_reverb, None)], [5000], x[s])
+        assert np.array_equal(expect, y[s])
+        different = _expected(checker, F.mono, 48000, [(T.eax_reverb, None)], H.blocks_of(5000, 1024), x[s])
+        assert not np.array_equal(different, y[s])  # the partition matters for the reverb
+
+
+def test_integer_state_is_bit_exact():
+    """Ring offsets, reverb fade counter and modulator index follow the reference's formulas
+    (offset_ += n, oalsfxpp.cpp:7853; fade 128 samples, :6118-6138; index % range, :7457)."""
+    lib = H.emu_lib()
+    rate, frames = 48000, [1024, 100, 2048, 77]
+    mod_time = 0.25
+    with ox.Engine(2, F.stereo, rate, 3, lib=lib) as eng:
+        eng.set_effect(0, T.eax_reverb, ox.default_props(T.eax_reverb, lib=lib, modulation_depth_=0.3, modulation_time_=mod_time))
+        eng.set_effect(1, T.ring_modulator)
+        eng.set_effect(2, T.chorus)
+        total = 0
+        for n in frames:
+            eng.mix(np.zeros((2, n, 2), np.float32))
+            total += n
+            st = eng.debug_state(1, 0)
+            assert st["offset"] == total
+            assert st["fade_count"] == min(total, 128)
+            assert st["mod_index"] == total % int(mod_time * rate)
+            step = int(np.float32(440.0) * np.float32(1 << 24) / np.float32(rate))
+            assert eng.debug_state(1, 1)["ring_mod_index"] == (total * step) & 0xFFFFFF
+            assert eng.debug_state(0, 2)["offset"] == total
+
+
+def test_bus_reduce_matches_float64_sum():
+    lib = H.emu_lib()
+    S, n = 40, 256
+    x = np.stack([H.noise(s, 2, n) for s in range(S)])
+    with ox.Engine(S, F.stereo, 48000, 1, lib=lib) as eng:
+        eng.set_effect(0, T.echo)
+        y = eng.mix(x)
+        bus = np.zeros((n, 2), np.float32)
+        eng.reduce_bus(n, y, bus)
+    want = y.astype(np.float64).sum(axis=0)
+    assert np.max(np.abs(bus - want)) <= 1e-5 * np.sqrt(S)
+
+
+def test_engine_argument_errors():
+    lib = H.emu_lib()
+    with pytest.raises(ox.OalsfxError) as e:
+        ox.Engine(1, 0, 48000, 1, lib=lib)
+    assert e.value.message == "Invalid channel format."
+    with pytest.raises(ox.OalsfxError) as e:
+        ox.Engine(1, F.mono, 7999, 1, lib=lib)
+    assert e.value.message == "Sampling rate is out of range."
+    with pytest.raises(ox.OalsfxError) as e:
+        ox.Engine(1, F.mono, 48000, 5, lib=lib)
+    assert e.value.message == "Effect count is out of range."
+    with ox.Engine(4, F.mono, 48000, 2, lib=lib) as eng:
+        with pytest.raises(ox.OalsfxError):
+            eng.set_effect(2, T.echo)
+        with pytest.raises(ox.OalsfxError):
+            eng.set_effect(0, T.echo, first_stream=3, n_streams=2)
+        assert eng.mix(np.zeros((4, 0, 1), np.float32), frames=0).size == 0  # zero frames is a no-op
