@@ -11,6 +11,7 @@
 
 #include "backend.h"
 #include "kernel_table.h"
+#include "quad.cuh"
 
 namespace oalsfx {
 namespace {
@@ -170,11 +171,16 @@ public:
 		case id: mix_kernel<CT, SF, F0, F1, F2, F3><<<blocks, threads, 0, st>>>(args); break;
 			OALSFX_KERNEL_TABLE(OALSFX_X)
 #undef OALSFX_X
+#define OALSFX_QX(id, CT, Q0, Q1, Q2, Q3, twin) \
+		case id: quad::quad_kernel<CT, quad::Q0, quad::Q1, quad::Q2, quad::Q3> \
+			<<<static_cast<unsigned>(args.tile_count), 128, 0, st>>>(args); break;
+			OALSFX_QUAD_TABLE(OALSFX_QX)
+#undef OALSFX_QX
 		default:
 			error_ = "unknown kernel id";
 			return false;
 		}
-		return check(cudaGetLastError(), kernel_infos()[kernel_id].name);
+		return check(cudaGetLastError(), kernel_name(kernel_id));
 	}
 
 	bool reduce_bus(const float* data, long long ts, long long ls, long long fs, long long cs,

@@ -16,6 +16,7 @@
 #include "oalsfx_engine.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -60,6 +61,7 @@ struct GroupKey {
 struct Group {
 	GroupKey key;
 	bool identity = false;     // covers tiles 0..T-1 with all lanes
+	bool full_tiles = false;   // every listed tile takes part with all of its (existing) lanes
 	size_t tile_begin = 0;     // into the concatenated tile list
 	int tile_count = 0;
 };
@@ -97,6 +99,7 @@ struct oalsfx_engine {
 	std::vector<Group> groups;
 	bool groups_dirty = true;
 	long long launches = 0;
+	bool use_quad = true;               // OALSFX_NO_QUAD=1 forces the thread-per-stream kernels (A/B measurements)
 	std::string error;
 
 	~oalsfx_engine()
@@ -355,6 +358,12 @@ struct oalsfx_engine {
 			g.key = kv.first;
 			g.tile_begin = all.size();
 			g.tile_count = static_cast<int>(kv.second.size());
+			g.full_tiles = true;
+			for (const TileRef& t : kv.second) {
+				const int lanes_here = std::min(kLanes, streams - static_cast<int>(t.tile) * kLanes);
+				const uint32_t want = (lanes_here == kLanes ? 0xFFFFFFFFU : ((1U << lanes_here) - 1U));
+				g.full_tiles = g.full_tiles && t.mask == want;
+			}
 			all.insert(all.end(), kv.second.begin(), kv.second.end());
 			groups.push_back(g);
 		}
@@ -449,7 +458,10 @@ struct oalsfx_engine {
 				}
 			}
 			++launches;
-			return be->launch_mix(ki.id, a, stream);
+			// All lanes of every tile take part (ragged tail apart): the 4-lanes-per-stream kernel.
+			const int quad_id = quad_for_twin(ki.id);
+			const bool whole_tiles = g.identity || g.full_tiles;
+			return be->launch_mix((quad_id >= 0 && whole_tiles && use_quad) ? quad_id : ki.id, a, stream);
 		}
 		// Chain of single-effect passes: the dry pass carries the first non-null slot.
 		static const int gen_for_kind[] = {kGenDry, kGenModDelay, kGenCompressor, kGenDedicated, kGenDistortion,
@@ -520,6 +532,7 @@ int oalsfx_engine_create(const oalsfx_engine_desc* desc, oalsfx_engine** out)
 	e->tiles = (desc->num_streams + kLanes - 1) / kLanes;
 	e->channels = dev.channels;
 	e->slots = desc->effect_count;
+	e->use_quad = std::getenv("OALSFX_NO_QUAD") == nullptr;
 	e->be = make_backend(desc->device, g_create_error);
 	if (!e->be) {
 		delete e;

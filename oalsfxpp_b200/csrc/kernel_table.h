@@ -32,14 +32,48 @@
 	/* cfg0: one echo slot, stereo */ \
 	X(kEchoStereo, 2, false, FxEcho, FxNull, FxNull, FxNull)
 
+// Quad kernels (quad.cuh: four lanes per stream, next-sample prefetch) -- the throughput path.
+// QX(id, CT, Q0, Q1, Q2, Q3, twin): `twin` is the thread-per-stream entry with the same signature;
+// the engine launches the quad kernel instead of its twin whenever every tile of the group takes
+// part with all its lanes.  (The CPU test build has no quad kernels and runs the twin.)
+#define OALSFX_QUAD_TABLE(QX) \
+	QX(kQuadChainStereo, 2, QEqualizer, QModDelay, QEcho, QReverb, kChainStereo) \
+	QX(kQuadChain2Mono, 1, QModDelay, QRingMod, QDistortion, QCompressor, kChain2Mono) \
+	QX(kQuadReverbMono, 1, QReverb, QNull, QNull, QNull, kReverbMono) \
+	QX(kQuadEchoStereo, 2, QEcho, QNull, QNull, QNull, kEchoStereo)
+
 namespace oalsfx {
 
 enum KernelId : int {
 #define OALSFX_X(id, CT, SF, F0, F1, F2, F3) id,
 	OALSFX_KERNEL_TABLE(OALSFX_X)
 #undef OALSFX_X
-	kKernelCount
+	kKernelCount,
+	kQuadFirst = kKernelCount - 1,
+#define OALSFX_QX(id, CT, Q0, Q1, Q2, Q3, twin) id,
+	OALSFX_QUAD_TABLE(OALSFX_QX)
+#undef OALSFX_QX
+	kKernelEnd
 };
+
+// quad kernel id for a thread-per-stream twin id, or -1
+inline int quad_for_twin(int twin_id)
+{
+#define OALSFX_QX(id, CT, Q0, Q1, Q2, Q3, twin) if (twin_id == twin) return id;
+	OALSFX_QUAD_TABLE(OALSFX_QX)
+#undef OALSFX_QX
+	return -1;
+}
+
+inline int twin_of_quad(int quad_id)
+{
+#define OALSFX_QX(id, CT, Q0, Q1, Q2, Q3, twin) if (quad_id == id) return twin;
+	OALSFX_QUAD_TABLE(OALSFX_QX)
+#undef OALSFX_QX
+	return -1;
+}
+
+inline const char* kernel_name(int id);
 
 // Effect "kind" = which processor handles an FxType (chorus/flanger and reverb/EAX share one).
 enum FxKind : int { kKindNull, kKindModDelay, kKindCompressor, kKindDedicated, kKindDistortion, kKindEcho,
@@ -82,6 +116,17 @@ inline const KernelInfo* kernel_infos()
 #undef OALSFX_X
 	};
 	return infos;
+}
+
+inline const char* kernel_name(int id)
+{
+	if (id >= 0 && id < kKernelCount) {
+		return kernel_infos()[id].name;
+	}
+#define OALSFX_QX(qid, CT, Q0, Q1, Q2, Q3, twin) if (id == qid) return #qid;
+	OALSFX_QUAD_TABLE(OALSFX_QX)
+#undef OALSFX_QX
+	return "?";
 }
 
 } // namespace oalsfx

@@ -48,6 +48,9 @@ public:
 	}
 	bool launch_mix(int kernel_id, const MixArgs& a, void*) override
 	{
+		if (kernel_id >= kKernelCount) { // a quad kernel: the CPU build runs its thread-per-stream twin
+			kernel_id = twin_of_quad(kernel_id);
+		}
 		for (int w = 0; w < a.tile_count; ++w) {
 			int tile = w;
 			uint32_t mask = 0xFFFFFFFFU;
