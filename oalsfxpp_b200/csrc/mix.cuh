@@ -10,6 +10,8 @@
 #ifndef OALSFX_MIX_CUH
 #define OALSFX_MIX_CUH
 
+#include <type_traits>
+
 #include "fx.cuh"
 
 namespace oalsfx {
@@ -91,11 +93,12 @@ struct SlotRunner {
 	Fx fx;
 	SendHist hist[SF ? kMaxChannels : 1];
 
-	OALSFX_HD void begin(const MixArgs& a, int p, int tile, int lane)
+	OALSFX_HD void begin(const MixArgs& a, int p, int tile, int lane, float* prefetch_column)
 	{
 		if (Fx::kIsNull) {
 			return;
 		}
+		fx.set_prefetch(prefetch_column);
 		uint32_t* st = a.slot_state[p] + (static_cast<long long>(tile) * kSlotStateWords) * kLanes + lane;
 		float* ring = a.ring[p] ? a.ring[p] + static_cast<long long>(tile) * a.ring_tile_stride[p] + lane : nullptr;
 		fx.template begin<CT>(a.slot[p], st, ring, (a.update_mask >> p) & 1U, a.frames, a.channels);
@@ -136,7 +139,7 @@ struct SlotRunner {
 			return;
 		}
 		uint32_t* st = a.slot_state[p] + (static_cast<long long>(tile) * kSlotStateWords) * kLanes + lane;
-		fx.end(a.slot[p], st);
+		fx.template end_ct<CT>(a.slot[p], st, a.channels);
 		uint32_t* ss = a.send_state + (static_cast<long long>(tile) * kSendStateWords +
 			(1 + a.aux_index[p]) * kMaxChannels * 8) * kLanes + lane;
 		for (int c = 0; c < a.channels; ++c) {
@@ -154,9 +157,19 @@ struct SlotRunner {
 
 // Whole block for one stream.  SF = false requires: no send has an active shelf filter and
 // frames >= 2 (then every processed send's filter history is simply the last two input samples).
+// Which slot position (if any) owns the warp's prefetch window: the first reverb.
+template <class F0, class F1, class F2, class F3>
+struct PrefetchUser {
+	static constexpr int value = std::is_same<F0, FxReverb>::value ? 0 : std::is_same<F1, FxReverb>::value ? 1 :
+		std::is_same<F2, FxReverb>::value ? 2 : std::is_same<F3, FxReverb>::value ? 3 : -1;
+};
+
+// `prefetch_column`: this thread's column of its warp's shared-memory prefetch window (kPfWarpFloats
+// floats per warp), or null (CPU test build, kernels without a window) to read the rings directly.
 template <int CT, bool SF, class F0, class F1, class F2, class F3>
-OALSFX_HD void mix_stream(const MixArgs& a, int tile, int lane)
+OALSFX_HD void mix_stream(const MixArgs& a, int tile, int lane, float* prefetch_column = nullptr)
 {
+	constexpr int pf_user = PrefetchUser<F0, F1, F2, F3>::value;
 	const int channels = CT ? CT : a.channels;
 	const float* src = a.src + tile * a.io_ts + lane * a.io_ls;
 	float* dst = a.dst + tile * a.io_ts + lane * a.io_ls;
@@ -165,10 +178,10 @@ OALSFX_HD void mix_stream(const MixArgs& a, int tile, int lane)
 	SlotRunner<CT, SF, F1> r1;
 	SlotRunner<CT, SF, F2> r2;
 	SlotRunner<CT, SF, F3> r3;
-	r0.begin(a, 0, tile, lane);
-	r1.begin(a, 1, tile, lane);
-	r2.begin(a, 2, tile, lane);
-	r3.begin(a, 3, tile, lane);
+	r0.begin(a, 0, tile, lane, pf_user == 0 ? prefetch_column : nullptr);
+	r1.begin(a, 1, tile, lane, pf_user == 1 ? prefetch_column : nullptr);
+	r2.begin(a, 2, tile, lane, pf_user == 2 ? prefetch_column : nullptr);
+	r3.begin(a, 3, tile, lane, pf_user == 3 ? prefetch_column : nullptr);
 
 	SendHist dhist[SF ? kMaxChannels : 1];
 	uint32_t* dss = a.send_state + (static_cast<long long>(tile) * kSendStateWords) * kLanes + lane;
@@ -245,6 +258,8 @@ OALSFX_HD void mix_stream(const MixArgs& a, int tile, int lane)
 template <int CT, bool SF, class F0, class F1, class F2, class F3>
 __global__ void __launch_bounds__(64) mix_kernel(const __grid_constant__ MixArgs a)
 {
+	constexpr bool has_window = PrefetchUser<F0, F1, F2, F3>::value >= 0;
+	__shared__ float window[has_window ? (64 / kLanes) * kPfWarpFloats : 1];
 	const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / kLanes;
 	const int lane = threadIdx.x % kLanes;
 	if (warp >= a.tile_count) {
@@ -260,7 +275,7 @@ __global__ void __launch_bounds__(64) mix_kernel(const __grid_constant__ MixArgs
 	if (!((mask >> lane) & 1U) || tile * kLanes + lane >= a.num_streams) {
 		return;
 	}
-	mix_stream<CT, SF, F0, F1, F2, F3>(a, tile, lane);
+	mix_stream<CT, SF, F0, F1, F2, F3>(a, tile, lane, has_window ? window + (threadIdx.x / kLanes) * kPfWarpFloats + lane : nullptr);
 }
 #endif
 
