@@ -12,6 +12,7 @@
 #include "backend.h"
 #include "kernel_table.h"
 #include "quad.cuh"
+#include "duo.cuh"
 
 namespace oalsfx {
 namespace {
@@ -176,6 +177,10 @@ public:
 			<<<static_cast<unsigned>(args.tile_count), 128, 0, st>>>(args); break;
 			OALSFX_QUAD_TABLE(OALSFX_QX)
 #undef OALSFX_QX
+#define OALSFX_DX(id, CT, F0, F1, F2, F3, twin) \
+		case id: duo::duo_kernel<CT, F0, F1, F2, F3><<<static_cast<unsigned>(args.tile_count), 64, 0, st>>>(args); break;
+			OALSFX_DUO_TABLE(OALSFX_DX)
+#undef OALSFX_DX
 		default:
 			error_ = "unknown kernel id";
 			return false;

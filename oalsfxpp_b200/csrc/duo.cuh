@@ -1,0 +1,190 @@
+// duo.cuh -- the fused 4-slot kernel as TWO specialised warps per 32-stream tile.
+//
+// One thread still owns one stream (coefficients stay warp-uniform constant-bank operands, every
+// ring access of a warp is one full 128-byte line), but the slots are split over two warps so that
+// each keeps only its own recurrent state in registers:
+//
+//   front warp : source encode + dry mix + slots 0..2        (cfg4: equalizer, chorus, echo)
+//   back  warp : slot 3 + output                             (cfg4: EAX reverb, 24-read cp.async window)
+//
+// The front warp hands the input frame and the partially summed bus to the back warp through a
+// double-buffered shared-memory exchange (kDuoChunk frames per hand-off, named barriers), so the
+// bus never touches HBM and the per-sample summation order stays dry, slot 0, 1, 2, 3 -- exactly
+// the reference's (oalsfxpp.cpp:2984-3037).  Per-thread registers drop from ~240 to ~130/~160,
+// which doubles the warps in flight, and the two halves of a stream's work overlap in time.
+//
+// Host-checked requirements (as for the quad kernels): no send shelf filter active, frames >= 2,
+// every tile of the launch takes part with all of its lanes.
+#ifndef OALSFX_DUO_CUH
+#define OALSFX_DUO_CUH
+
+#if defined(__CUDACC__)
+
+#include "mix.cuh"
+
+namespace oalsfx {
+namespace duo {
+
+constexpr int kDuoChunk = 16;          // frames per hand-off
+constexpr int kBarFull = 1;            // named barriers 1,2: buffer b filled by the front warp
+constexpr int kBarEmpty = 3;           // named barriers 3,4: buffer b drained by the back warp
+
+__device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+
+template <int CT>
+__device__ __forceinline__ void store_passthrough_history(uint32_t* ss, int send, const float* src, const MixArgs& a, bool io_ok)
+{
+	// No shelf filter active: a processed send's filter histories are the last two input samples
+	// (oalsfxpp.cpp:1038-1056).
+#pragma unroll
+	for (int c = 0; c < CT; ++c) {
+		const float last1 = io_ok ? src[(a.frames - 1) * a.io_fs + c * a.io_cs] : 0.0F;
+		const float last2 = io_ok ? src[(a.frames - 2) * a.io_fs + c * a.io_cs] : 0.0F;
+		SendHist h;
+		h.lp.x0 = h.lp.y0 = h.hp.x0 = h.hp.y0 = last1;
+		h.lp.x1 = h.lp.y1 = h.hp.x1 = h.hp.y1 = last2;
+		store_words(h, ss + (send * kMaxChannels + c) * 8 * kLanes);
+	}
+}
+
+template <int CT, class F0, class F1, class F2, class F3>
+__global__ void __launch_bounds__(64) duo_kernel(const __grid_constant__ MixArgs a)
+{
+	constexpr bool back_has_window = std::is_same<F3, FxReverb>::value;
+	__shared__ float window[back_has_window ? kPfWarpFloats : 1];
+	__shared__ float xch[2][kDuoChunk][2 * CT][kLanes]; // [buffer][frame][x_0..x_C-1, bus_0..bus_C-1][lane]
+	__shared__ float fwin[kFwWarpFloats];               // front warp: chorus/echo taps and input frames in flight
+	static_assert(4 + CT <= kFwTaps, "front window too small for this channel count");
+
+	const int tile = a.tiles ? static_cast<int>(a.tiles[blockIdx.x].tile) : static_cast<int>(blockIdx.x);
+	const int lane = threadIdx.x % kLanes;
+	const bool front = threadIdx.x < kLanes;
+	const bool io_ok = tile * kLanes + lane < a.num_streams;
+	const float* src = a.src + tile * a.io_ts + lane * a.io_ls;
+	float* dst = a.dst + tile * a.io_ts + lane * a.io_ls;
+	uint32_t* ss = a.send_state + (static_cast<long long>(tile) * kSendStateWords) * kLanes + lane;
+	const int chunks = (a.frames + kDuoChunk - 1) / kDuoChunk;
+
+	if (front) {
+		SlotRunner<CT, false, F0> r0;
+		SlotRunner<CT, false, F1> r1;
+		SlotRunner<CT, false, F2> r2;
+		// Window taps: 0,1 = the first chorus/flanger, 2,3 = the first echo, 4.. = input channels.
+		constexpr bool m0 = std::is_same<F0, FxModDelay>::value, m1 = std::is_same<F1, FxModDelay>::value && !m0,
+			m2 = std::is_same<F2, FxModDelay>::value && !m0 && !m1;
+		constexpr bool e0 = std::is_same<F0, FxEcho>::value, e1 = std::is_same<F1, FxEcho>::value && !e0,
+			e2 = std::is_same<F2, FxEcho>::value && !e0 && !e1;
+		float* col = fwin + lane;
+		r0.begin(a, 0, tile, lane, m0 ? col : e0 ? col + 2 * kLanes : nullptr);
+		r1.begin(a, 1, tile, lane, m1 ? col : e1 ? col + 2 * kLanes : nullptr);
+		r2.begin(a, 2, tile, lane, m2 ? col : e2 ? col + 2 * kLanes : nullptr);
+		// Everything long-latency of sample i + kFwDepth is requested while sample i is computed.
+		auto issue = [&](int ahead, int frame) {
+			r0.fx.prefetch_issue(a.slot[0], ahead);
+			r1.fx.prefetch_issue(a.slot[1], ahead);
+			r2.fx.prefetch_issue(a.slot[2], ahead);
+			if (io_ok && frame < a.frames) {
+#pragma unroll
+				for (int c = 0; c < CT; ++c) {
+					cp_async_f32(col + (frame & (kFwSlots - 1)) * kFwSlotFloats + (4 + c) * kLanes, src + frame * a.io_fs + c * a.io_cs);
+				}
+			}
+			cp_async_commit_group();
+		};
+		for (int k = 0; k < kFwDepth; ++k) {
+			issue(k, k);
+		}
+		for (int ci = 0; ci < chunks; ++ci) {
+			const int b = ci & 1;
+			const int first = ci * kDuoChunk;
+			const int count = min(kDuoChunk, a.frames - first);
+			bar_sync(kBarEmpty + b);
+			for (int f = 0; f < count; ++f) {
+				const int i = first + f;
+				float x[CT], acc[CT];
+				issue(kFwDepth, i + kFwDepth);
+				cp_async_wait_group<kFwDepth>();
+#pragma unroll
+				for (int c = 0; c < CT; ++c) {
+					x[c] = io_ok ? col[(i & (kFwSlots - 1)) * kFwSlotFloats + (4 + c) * kLanes] : 0.0F;
+					acc[c] = 0.0F;
+				}
+				// direct send (oalsfxpp.cpp:2924-2950)
+#pragma unroll
+				for (int c = 0; c < CT; ++c) {
+#pragma unroll
+					for (int k = 0; k < CT; ++k) {
+						if (audible(a.direct.gains[c][k])) {
+							acc[k] += x[c] * a.direct.gains[c][k];
+						}
+					}
+				}
+				r0.step(a, 0, x, acc);
+				r1.step(a, 1, x, acc);
+				r2.step(a, 2, x, acc);
+#pragma unroll
+				for (int c = 0; c < CT; ++c) {
+					xch[b][f][c][lane] = x[c];
+					xch[b][f][CT + c][lane] = acc[c];
+				}
+			}
+			__threadfence_block();
+			bar_arrive(kBarFull + b);
+		}
+		cp_async_wait_group<0>();
+		r0.end_state_only(a, 0, tile, lane);
+		r1.end_state_only(a, 1, tile, lane);
+		r2.end_state_only(a, 2, tile, lane);
+		store_passthrough_history<CT>(ss, 0, src, a, io_ok);
+		if (!F0::kIsNull) {
+			store_passthrough_history<CT>(ss, 1 + a.aux_index[0], src, a, io_ok);
+		}
+		if (!F1::kIsNull) {
+			store_passthrough_history<CT>(ss, 1 + a.aux_index[1], src, a, io_ok);
+		}
+		if (!F2::kIsNull) {
+			store_passthrough_history<CT>(ss, 1 + a.aux_index[2], src, a, io_ok);
+		}
+	} else {
+		SlotRunner<CT, false, F3> r3;
+		r3.begin(a, 3, tile, lane, back_has_window ? window + lane : nullptr);
+		bar_arrive(kBarEmpty + 0);
+		bar_arrive(kBarEmpty + 1);
+		for (int ci = 0; ci < chunks; ++ci) {
+			const int b = ci & 1;
+			const int first = ci * kDuoChunk;
+			const int count = min(kDuoChunk, a.frames - first);
+			bar_sync(kBarFull + b);
+			for (int f = 0; f < count; ++f) {
+				const int i = first + f;
+				float x[CT], acc[CT];
+#pragma unroll
+				for (int c = 0; c < CT; ++c) {
+					x[c] = xch[b][f][c][lane];
+					acc[c] = xch[b][f][CT + c][lane];
+				}
+				r3.step(a, 3, x, acc);
+				if (io_ok) {
+#pragma unroll
+					for (int c = 0; c < CT; ++c) {
+						dst[i * a.io_fs + c * a.io_cs] = acc[c];
+					}
+				}
+			}
+			if (ci + 2 < chunks) {
+				bar_arrive(kBarEmpty + b); // nobody waits for the last two drains
+			}
+		}
+		r3.end_state_only(a, 3, tile, lane);
+		if (!F3::kIsNull) {
+			store_passthrough_history<CT>(ss, 1 + a.aux_index[3], src, a, io_ok);
+		}
+	}
+}
+
+} // namespace duo
+} // namespace oalsfx
+
+#endif // __CUDACC__
+#endif

@@ -99,7 +99,9 @@ struct oalsfx_engine {
 	std::vector<Group> groups;
 	bool groups_dirty = true;
 	long long launches = 0;
-	bool use_quad = true;               // OALSFX_NO_QUAD=1 forces the thread-per-stream kernels (A/B measurements)
+	// Which fused kernel family serves whole-tile groups: 2 = duo (default), 1 = quad, 0 = the plain
+	// thread-per-stream twin.  OALSFX_KERNEL=duo|quad|single overrides (A/B measurements only).
+	int family = 2;
 	std::string error;
 
 	~oalsfx_engine()
@@ -459,9 +461,14 @@ struct oalsfx_engine {
 			}
 			++launches;
 			// All lanes of every tile take part (ragged tail apart): the 4-lanes-per-stream kernel.
-			const int quad_id = quad_for_twin(ki.id);
 			const bool whole_tiles = g.identity || g.full_tiles;
-			return be->launch_mix((quad_id >= 0 && whole_tiles && use_quad) ? quad_id : ki.id, a, stream);
+			int id = ki.id;
+			if (whole_tiles && family == 2 && duo_for_twin(ki.id) >= 0) {
+				id = duo_for_twin(ki.id);
+			} else if (whole_tiles && family >= 1 && quad_for_twin(ki.id) >= 0) {
+				id = quad_for_twin(ki.id);
+			}
+			return be->launch_mix(id, a, stream);
 		}
 		// Chain of single-effect passes: the dry pass carries the first non-null slot.
 		static const int gen_for_kind[] = {kGenDry, kGenModDelay, kGenCompressor, kGenDedicated, kGenDistortion,
@@ -532,7 +539,9 @@ int oalsfx_engine_create(const oalsfx_engine_desc* desc, oalsfx_engine** out)
 	e->tiles = (desc->num_streams + kLanes - 1) / kLanes;
 	e->channels = dev.channels;
 	e->slots = desc->effect_count;
-	e->use_quad = std::getenv("OALSFX_NO_QUAD") == nullptr;
+	if (const char* fam = std::getenv("OALSFX_KERNEL")) {
+		e->family = (std::strcmp(fam, "single") == 0 ? 0 : std::strcmp(fam, "quad") == 0 ? 1 : 2);
+	}
 	e->be = make_backend(desc->device, g_create_error);
 	if (!e->be) {
 		delete e;

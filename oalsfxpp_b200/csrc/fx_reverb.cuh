@@ -30,17 +30,6 @@ constexpr int kPfDepth = kPfSlots - 1;      // samples in flight beyond the curr
 constexpr int kPfTaps = 24;
 constexpr int kPfWarpFloats = kPfSlots * kPfTaps * kLanes; // 12 KiB per reverb warp
 
-#if defined(__CUDA_ARCH__)
-__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_src)
-{
-	const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
-	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-#endif
-
 struct FxReverb {
 	// Layout of the slot state in HBM (words, per lane).  Only the hot part lives in registers.
 	struct State {
@@ -80,6 +69,7 @@ struct FxReverb {
 	bool primed, can_pf;
 
 	OALSFX_HD void set_prefetch(float* column) { pf_col = column; }
+	OALSFX_HD void prefetch_issue(const SlotCoef&, int) {} // the reverb runs its own pipeline inside step()
 
 	OALSFX_HD int32_t old_tap(int group, int line) const
 	{

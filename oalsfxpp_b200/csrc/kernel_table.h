@@ -42,6 +42,11 @@
 	QX(kQuadReverbMono, 1, QReverb, QNull, QNull, QNull, kReverbMono) \
 	QX(kQuadEchoStereo, 2, QEcho, QNull, QNull, QNull, kEchoStereo)
 
+// Duo kernels (duo.cuh: thread per stream, front warp = dry + slots 0..2, back warp = slot 3 +
+// output, shared-memory hand-off).  DX(id, CT, F0, F1, F2, F3, twin), same twin rule as above.
+#define OALSFX_DUO_TABLE(DX) \
+	DX(kDuoChainStereo, 2, FxEqualizer, FxModDelay, FxEcho, FxReverb, kChainStereo)
+
 namespace oalsfx {
 
 enum KernelId : int {
@@ -53,8 +58,20 @@ enum KernelId : int {
 #define OALSFX_QX(id, CT, Q0, Q1, Q2, Q3, twin) id,
 	OALSFX_QUAD_TABLE(OALSFX_QX)
 #undef OALSFX_QX
+#define OALSFX_DX(id, CT, F0, F1, F2, F3, twin) id,
+	OALSFX_DUO_TABLE(OALSFX_DX)
+#undef OALSFX_DX
 	kKernelEnd
 };
+
+// duo kernel id for a thread-per-stream twin id, or -1
+inline int duo_for_twin(int twin_id)
+{
+#define OALSFX_DX(id, CT, F0, F1, F2, F3, twin) if (twin_id == twin) return id;
+	OALSFX_DUO_TABLE(OALSFX_DX)
+#undef OALSFX_DX
+	return -1;
+}
 
 // quad kernel id for a thread-per-stream twin id, or -1
 inline int quad_for_twin(int twin_id)
@@ -70,6 +87,9 @@ inline int twin_of_quad(int quad_id)
 #define OALSFX_QX(id, CT, Q0, Q1, Q2, Q3, twin) if (quad_id == id) return twin;
 	OALSFX_QUAD_TABLE(OALSFX_QX)
 #undef OALSFX_QX
+#define OALSFX_DX(id, CT, F0, F1, F2, F3, twin) if (quad_id == id) return twin;
+	OALSFX_DUO_TABLE(OALSFX_DX)
+#undef OALSFX_DX
 	return -1;
 }
 
@@ -126,6 +146,9 @@ inline const char* kernel_name(int id)
 #define OALSFX_QX(qid, CT, Q0, Q1, Q2, Q3, twin) if (id == qid) return #qid;
 	OALSFX_QUAD_TABLE(OALSFX_QX)
 #undef OALSFX_QX
+#define OALSFX_DX(did, CT, F0, F1, F2, F3, twin) if (id == did) return #did;
+	OALSFX_DUO_TABLE(OALSFX_DX)
+#undef OALSFX_DX
 	return "?";
 }
 

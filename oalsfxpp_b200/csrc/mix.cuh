@@ -133,6 +133,16 @@ struct SlotRunner {
 		fx.template step<CT>(a.slot[p], wet, acc, a.channels);
 	}
 
+	// Effect state only (the caller writes the send filter history itself).
+	OALSFX_HD void end_state_only(const MixArgs& a, int p, int tile, int lane)
+	{
+		if (Fx::kIsNull) {
+			return;
+		}
+		uint32_t* st = a.slot_state[p] + (static_cast<long long>(tile) * kSlotStateWords) * kLanes + lane;
+		fx.template end_ct<CT>(a.slot[p], st, a.channels);
+	}
+
 	OALSFX_HD void end(const MixArgs& a, int p, int tile, int lane, const float* last1, const float* last2)
 	{
 		if (Fx::kIsNull) {
