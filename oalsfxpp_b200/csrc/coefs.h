@@ -110,9 +110,15 @@ struct ReverbCoef {
 	const float* mod_sinus;            // device table [mod_range] of host-evaluated sin(tau*i/range), or null
 };
 
+// A shelf / peaking / pass filter whose reference frequency is >= rate/2 is unstable in the reference
+// itself (outputs run to Inf/NaN, e.g. the echo's 5 kHz shelf at 8 kHz).  Such slots are kept off the
+// "fast" kernels, whose unconditional `sample * 0` for skipped gains would spread a NaN to outputs
+// the reference leaves untouched.
+constexpr uint32_t kCoefUnstable = 1U;
+
 struct SlotCoef {
 	int32_t type;                      // FxType
-	uint32_t seq;                      // bumped once per reference `EffectState::update` call
+	uint32_t flags;                    // kCoefUnstable: a biquad was designed at or above Nyquist
 	union {
 		ModDelayCoef mod_delay;        // chorus, flanger
 		CompressorCoef compressor;

@@ -194,8 +194,13 @@ void identity_first_order_gains(const DeviceLayout& dev, float out[kWetChannels]
 // ---- biquad design (oalsfxpp.cpp:867-982, 1074-1090) ------------------------------------------
 enum BiquadKind { kHighShelf, kLowShelf, kPeaking, kLowPass, kHighPass, kBandPass };
 
+thread_local bool g_saw_unstable_design = false;
+
 Biquad design_biquad(BiquadKind kind, float gain, float freq_mult, float rcp_q)
 {
+	if (!(freq_mult < 0.5F)) {
+		g_saw_unstable_design = true;
+	}
 	const float w0 = kTau * freq_mult;
 	const float sin_w0 = std::sin(w0);
 	const float cos_w0 = std::cos(w0);
@@ -892,6 +897,11 @@ void derive_slot(
 	out.type = fx_type;
 	tables.sin_delays.clear();
 	tables.mod_sinus.clear();
+	g_saw_unstable_design = false;
+	struct FlagOnExit {
+		SlotCoef& c;
+		~FlagOnExit() { c.flags = g_saw_unstable_design ? kCoefUnstable : 0U; }
+	} flag_on_exit{out};
 	switch (fx_type) {
 	case kFxChorus: {
 		const auto& p = props.chorus_;

@@ -115,9 +115,7 @@ __global__ void __launch_bounds__(64) duo_kernel(const __grid_constant__ MixArgs
 				for (int c = 0; c < CT; ++c) {
 #pragma unroll
 					for (int k = 0; k < CT; ++k) {
-						if (audible(a.direct.gains[c][k])) {
-							acc[k] += x[c] * a.direct.gains[c][k];
-						}
+						acc[k] += x[c] * a.direct.gains[c][k]; // gains sanitized by the host
 					}
 				}
 				r0.step(a, 0, x, acc);

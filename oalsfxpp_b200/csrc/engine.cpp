@@ -16,6 +16,7 @@
 #include "oalsfx_engine.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -428,6 +429,36 @@ struct oalsfx_engine {
 		}
 	}
 
+	// Fast kernels add `sample * gain` unconditionally: make every static gain the reference would
+	// skip (|g| <= 1e-5, oalsfxpp.cpp:56) an exact zero so the sum is unchanged.
+	static void sanitize(float* gains, int n)
+	{
+		for (int i = 0; i < n; ++i) {
+			if (!(std::fabs(gains[i]) > kSilenceGain)) {
+				gains[i] = 0.0F;
+			}
+		}
+	}
+
+	static void sanitize_gains(MixArgs& a)
+	{
+		sanitize(&a.direct.gains[0][0], kMaxChannels * kMaxChannels);
+		for (int p = 0; p < kMaxSlots; ++p) {
+			sanitize(&a.aux[p].gains[0][0], kMaxChannels * kMaxChannels);
+			SlotCoef& sc = a.slot[p];
+			switch (kind_of_type(sc.type)) {
+			case kKindModDelay: sanitize(&sc.u.mod_delay.gains[0][0], 2 * kMaxChannels); break;
+			case kKindCompressor: sanitize(&sc.u.compressor.gains[0][0], kWetChannels * kMaxChannels); break;
+			case kKindDedicated: sanitize(sc.u.dedicated.gains, kMaxChannels); break;
+			case kKindDistortion: sanitize(sc.u.distortion.gains, kMaxChannels); break;
+			case kKindEcho: sanitize(&sc.u.echo.gains[0][0], 2 * kMaxChannels); break;
+			case kKindEqualizer: sanitize(&sc.u.equalizer.gains[0][0], kWetChannels * kMaxChannels); break;
+			case kKindRingMod: sanitize(&sc.u.ring_mod.gains[0][0], kWetChannels * kMaxChannels); break;
+			default: break; // reverb: its pan gains are running state, tested per sub-chunk on the device
+			}
+		}
+	}
+
 	bool launch_group(const Group& g, int frames, const float* src, float* dst, int layout,
 		long long frames_total, long long frame0, bool first_block, void* stream)
 	{
@@ -439,6 +470,9 @@ struct oalsfx_engine {
 			kinds[s] = kind_of_type(type);
 			if (kinds[s] != kKindNull && sc.aux_coef[s].filter_type != 0) {
 				any_filter = true;
+			}
+			if (classes[static_cast<size_t>(g.key.fx[s])].coef.flags & kCoefUnstable) {
+				any_filter = true; // keeps the group on the exact (generic) kernels, see coefs.h
 			}
 		}
 		// A fused single-pass kernel for this signature?
@@ -461,6 +495,7 @@ struct oalsfx_engine {
 			}
 			++launches;
 			// All lanes of every tile take part (ragged tail apart): the 4-lanes-per-stream kernel.
+			sanitize_gains(a);
 			const bool whole_tiles = g.identity || g.full_tiles;
 			int id = ki.id;
 			if (whole_tiles && family == 2 && duo_for_twin(ki.id) >= 0) {

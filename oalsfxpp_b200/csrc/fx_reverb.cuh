@@ -67,6 +67,7 @@ struct FxReverb {
 	const float* pf_cur;
 	int32_t pos_issue;
 	bool primed, can_pf;
+	bool pan_static;   // this sub-chunk: no gain ramps and every one of the 8 x C pan gains is audible
 
 	OALSFX_HD void set_prefetch(float* column) { pf_col = column; }
 	OALSFX_HD void prefetch_issue(const SlotCoef&, int) {} // the reverb runs its own pipeline inside step()
@@ -160,6 +161,7 @@ struct FxReverb {
 				c.late_tap[l] > c.late_feed_tap + kPfDepth && c.late_ap_off[l] > kPfDepth && c.late_off[l] > kPfDepth;
 		}
 		can_pf = ok;
+		pan_static = true;
 		const int counter = block_frames - base;
 		const float delta = 1.0F / static_cast<float>(counter);
 		ramp_mask[0] = ramp_mask[1] = 0;
@@ -176,10 +178,13 @@ struct FxReverb {
 					if (fabsf(step) > FLT_EPSILON) {
 						ramp_mask[l >> 2] |= bit;
 						step_gain[l][k] = step;
+						pan_static = false;
 					} else {
 						step_gain[l][k] = 0.0F;
 						if (audible(gain)) {
 							active_mask[l >> 2] |= bit;
+						} else {
+							pan_static = false;
 						}
 					}
 				}
@@ -228,9 +233,10 @@ struct FxReverb {
 	}
 
 	// Delay read (oalsfxpp.cpp:7358-7406): prefetched value, direct read, or old/new cross-fade.
+	template <bool PF>
 	OALSFX_HD float tap(int tap_index, int ring_word0, int mask, int pos, int group, int line, int new_d, float mu) const
 	{
-		if (pf_cur) {
+		if (PF) {
 			return pf_cur[tap_index * kLanes];
 		}
 		if (!faded) {
@@ -250,6 +256,7 @@ struct FxReverb {
 		v[3] = (x * f3) + (y * (-f0 + -f1 + -f2));
 	}
 
+	template <bool PF>
 	OALSFX_HD void vector_allpass(const ReverbCoef& c, float* vec, int ring_idx, int tap_base, int group,
 		const int32_t* new_off, int pos, float mu) const
 	{
@@ -259,7 +266,7 @@ struct FxReverb {
 		OALSFX_UNROLL
 		for (int i = 0; i < 4; ++i) {
 			const float input = vec[i];
-			vec[i] = tap(tap_base + i, word0 + i * len, c.mask[ring_idx], pos, group, i, new_off[i], mu) - (c.ap_feed_coeff * input);
+			vec[i] = tap<PF>(tap_base + i, word0 + i * len, c.mask[ring_idx], pos, group, i, new_off[i], mu) - (c.ap_feed_coeff * input);
 			f[i] = input + (c.ap_feed_coeff * vec[i]);
 		}
 		scatter(f, c.mix_x, c.mix_y);
@@ -288,7 +295,7 @@ struct FxReverb {
 	}
 #endif
 
-	template <int CT>
+	template <int CT, bool FAST = false>
 	OALSFX_HD void step(const SlotCoef& sc, const float* wet, float* acc, int channels)
 	{
 		const ReverbCoef& c = sc.u.reverb;
@@ -296,9 +303,6 @@ struct FxReverb {
 			begin_sub<CT>(c, channels);
 		}
 		const int pos = offset;
-		const float mu = fade;
-
-		pf_cur = nullptr;
 #if defined(__CUDA_ARCH__)
 		if (can_pf) {
 			if (!primed) {
@@ -311,10 +315,25 @@ struct FxReverb {
 			}
 			cp_async_wait_group<kPfDepth>();
 			pf_cur = pf_col + (pos & (kPfSlots - 1)) * (kPfTaps * kLanes);
+			body<CT, true>(c, wet, acc, channels, pos); // branch-free: every read is a shared-memory load
 		} else {
 			primed = false;
+			body<CT, false>(c, wet, acc, channels, pos);
 		}
+#else
+		body<CT, false>(c, wet, acc, channels, pos);
 #endif
+		sub_left -= 1;
+		if (sub_left == 0) {
+			end_sub<CT>(c, channels);
+		}
+	}
+
+	// One sample.  PF: all 24 ring reads come from the prefetch window (steady state).
+	template <int CT, bool PF>
+	OALSFX_HD void body(const ReverbCoef& c, const float* wet, float* acc, int channels, const int pos)
+	{
+		const float mu = fade;
 
 		const int main_len = c.mask[0] + 1, main0 = c.ring_base[0], main_mask = c.mask[0];
 		const int eline_len = c.mask[2] + 1, eline0 = c.ring_base[2], eline_mask = c.mask[2];
@@ -344,16 +363,16 @@ struct FxReverb {
 		// ---- early reflections (oalsfxpp.cpp:7625-7672) ----
 		OALSFX_UNROLL
 		for (int j = 0; j < 4; ++j) {
-			f[j] = tap(0 + j, main0 + j * main_len, main_mask, pos, 0, j, c.early_tap[j], mu) * c.early_tap_coeff[j];
+			f[j] = tap<PF>(0 + j, main0 + j * main_len, main_mask, pos, 0, j, c.early_tap[j], mu) * c.early_tap_coeff[j];
 		}
-		vector_allpass(c, f, 1, 4, 1, c.early_ap_off, pos, mu);
+		vector_allpass<PF>(c, f, 1, 4, 1, c.early_ap_off, pos, mu);
 		OALSFX_UNROLL
 		for (int j = 0; j < 4; ++j) {
 			ring.st(eline0 + j * eline_len + (pos & eline_mask), f[3 - j]); // delay_line_in4_rev
 		}
 		OALSFX_UNROLL
 		for (int j = 0; j < 4; ++j) {
-			f[j] += tap(8 + j, eline0 + j * eline_len, eline_mask, pos, 2, j, c.early_off[j], mu) * c.early_coeff[j];
+			f[j] += tap<PF>(8 + j, eline0 + j * eline_len, eline_mask, pos, 2, j, c.early_off[j], mu) * c.early_coeff[j];
 			early_out[j] = f[j];
 		}
 		{
@@ -369,7 +388,12 @@ struct FxReverb {
 		// calc_modulation_delays (oalsfxpp.cpp:7443-7470); when depth and filter are both zero the
 		// product range*sinus is +-0 and the delay is 0 whatever the sinus is.
 		int mod_delay = 0;
-		{
+		if (PF) { // can_pf implies depth == 0 and filter == 0: the delay is 0, only the index moves
+			mod_index += 1;
+			if (mod_index >= mod_range) {
+				mod_index = 0;
+			}
+		} else {
 			const bool quiet = (c.mod_depth == 0.0F && mod_filter == 0.0F);
 			const float sinus = (quiet ? 0.0F : c.mod_sinus[mod_index]);
 			mod_index += 1;
@@ -383,12 +407,12 @@ struct FxReverb {
 		}
 		OALSFX_UNROLL
 		for (int j = 0; j < 4; ++j) {
-			f[j] = tap(12 + j, main0 + j * main_len, main_mask, pos, 3, j, c.late_tap[j], mu) * c.density_gain;
+			f[j] = tap<PF>(12 + j, main0 + j * main_len, main_mask, pos, 3, j, c.late_tap[j], mu) * c.density_gain;
 		}
 		const int mod_pos = pos - mod_delay;
 		OALSFX_UNROLL
 		for (int j = 0; j < 4; ++j) {
-			f[j] += tap(16 + j, lline0 + j * lline_len, lline_mask, mod_pos, 5, j, c.late_off[j], mu);
+			f[j] += tap<PF>(16 + j, lline0 + j * lline_len, lline_mask, mod_pos, 5, j, c.late_off[j], mu);
 		}
 		OALSFX_UNROLL
 		for (int j = 0; j < 4; ++j) {
@@ -402,7 +426,7 @@ struct FxReverb {
 			t60[j][1][1] = o2;
 			f[j] = c.t60_mid[j] * o2;
 		}
-		vector_allpass(c, f, 3, 20, 4, c.late_ap_off, pos, mu);
+		vector_allpass<PF>(c, f, 3, 20, 4, c.late_ap_off, pos, mu);
 		OALSFX_UNROLL
 		for (int j = 0; j < 4; ++j) {
 			late_out[j] = f[j];
@@ -422,6 +446,19 @@ struct FxReverb {
 		}
 
 		// ---- pan the 8 line outputs to the bus with stepped gains (oalsfxpp.cpp:6142-6166, 2752-2798) ----
+		if (pan_static) {
+			OALSFX_UNROLL
+			for (int l = 0; l < 8; ++l) {
+				const float d = (l < 4 ? early_out[l] : late_out[l - 4]);
+				OALSFX_UNROLL
+				for (int k = 0; k < (CT ? CT : kMaxChannels); ++k) {
+					if (CT || k < channels) {
+						acc[k] += d * cur_gain[l][k];
+					}
+				}
+			}
+			return;
+		}
 		OALSFX_UNROLL
 		for (int l = 0; l < 8; ++l) {
 			const float d = (l < 4 ? early_out[l] : late_out[l - 4]);
@@ -439,10 +476,6 @@ struct FxReverb {
 			}
 		}
 
-		sub_left -= 1;
-		if (sub_left == 0) {
-			end_sub<CT>(c, channels);
-		}
 	}
 
 	template <int CT>

@@ -124,13 +124,13 @@ struct SlotRunner {
 				const float v = SF ? send_filter_step(sc, hist[SF ? c : 0], x[c]) : x[c];
 				OALSFX_UNROLL
 				for (int k = 0; k < kWetChannels; ++k) {
-					if (audible(sc.gains[c][k])) {
+					if (!SF || audible(sc.gains[c][k])) {
 						wet[k] += v * sc.gains[c][k];
 					}
 				}
 			}
 		}
-		fx.template step<CT>(a.slot[p], wet, acc, a.channels);
+		fx.template step<CT, !SF>(a.slot[p], wet, acc, a.channels);
 	}
 
 	// Effect state only (the caller writes the send filter history itself).
@@ -165,8 +165,9 @@ struct SlotRunner {
 	}
 };
 
-// Whole block for one stream.  SF = false requires: no send has an active shelf filter and
-// frames >= 2 (then every processed send's filter history is simply the last two input samples).
+// Whole block for one stream.  SF = false ("fast" kernels) requires: no send has an active shelf
+// filter, frames >= 2 (then every processed send's filter history is simply the last two input
+// samples) and static gains sanitized by the host (inaudible -> exact 0, see pan_add in fx.cuh).
 // Which slot position (if any) owns the warp's prefetch window: the first reverb.
 template <class F0, class F1, class F2, class F3>
 struct PrefetchUser {
@@ -227,7 +228,7 @@ OALSFX_HD void mix_stream(const MixArgs& a, int tile, int lane, float* prefetch_
 					const float v = SF ? send_filter_step(a.direct, dhist[SF ? c : 0], x[c]) : x[c];
 					OALSFX_UNROLL
 					for (int k = 0; k < (CT ? CT : kMaxChannels); ++k) {
-						if ((CT || k < channels) && audible(a.direct.gains[c][k])) {
+						if ((CT || k < channels) && (!SF || audible(a.direct.gains[c][k]))) {
 							acc[k] += v * a.direct.gains[c][k];
 						}
 					}
