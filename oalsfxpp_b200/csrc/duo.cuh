@@ -51,9 +51,17 @@ __device__ __forceinline__ void store_passthrough_history(uint32_t* ss, int send
 template <int CT, class F0, class F1, class F2, class F3>
 __global__ void __launch_bounds__(64) duo_kernel(const __grid_constant__ MixArgs a)
 {
+	// A reverb in slot 3 is split: its input stage (B->A conversion, shelf filters, main-line feed,
+	// ~150 of its ~830 instructions per sample) runs in the front warp, which balances the two warps.
+	// The front warp runs at most two hand-offs (32 frames) ahead; the main ring keeps 256 spare frames
+	// beyond its longest tap (oalsfxpp.cpp:6573), so feeding it early cannot overwrite a pending read.
 	constexpr bool back_has_window = std::is_same<F3, FxReverb>::value;
+	constexpr bool split_reverb = back_has_window;
+	using Front3 = typename std::conditional<split_reverb, FxReverbInput, FxNull>::type;
+	using Back3 = typename std::conditional<split_reverb, FxReverbTail, F3>::type;
 	__shared__ float window[back_has_window ? kPfWarpFloats : 1];
-	__shared__ float xch[2][kDuoChunk][2 * CT][kLanes]; // [buffer][frame][x_0..x_C-1, bus_0..bus_C-1][lane]
+	constexpr int kBusAt = split_reverb ? 0 : CT;       // the input frame is only carried when the back warp needs it
+	__shared__ float xch[2][kDuoChunk][kBusAt + CT][kLanes]; // [buffer][frame][(x_0..x_C-1,) bus_0..bus_C-1][lane]
 	__shared__ float fwin[kFwWarpFloats];               // front warp: chorus/echo taps and input frames in flight
 	static_assert(4 + CT <= kFwTaps, "front window too small for this channel count");
 
@@ -70,6 +78,8 @@ __global__ void __launch_bounds__(64) duo_kernel(const __grid_constant__ MixArgs
 		SlotRunner<CT, false, F0> r0;
 		SlotRunner<CT, false, F1> r1;
 		SlotRunner<CT, false, F2> r2;
+		SlotRunner<CT, false, Front3> r3in;
+		r3in.begin(a, 3, tile, lane, nullptr);
 		// Window taps: 0,1 = the first chorus/flanger, 2,3 = the first echo, 4.. = input channels.
 		constexpr bool m0 = std::is_same<F0, FxModDelay>::value, m1 = std::is_same<F1, FxModDelay>::value && !m0,
 			m2 = std::is_same<F2, FxModDelay>::value && !m0 && !m1;
@@ -121,10 +131,13 @@ __global__ void __launch_bounds__(64) duo_kernel(const __grid_constant__ MixArgs
 				r0.step(a, 0, x, acc);
 				r1.step(a, 1, x, acc);
 				r2.step(a, 2, x, acc);
+				r3in.step(a, 3, x, acc);
 #pragma unroll
 				for (int c = 0; c < CT; ++c) {
-					xch[b][f][c][lane] = x[c];
-					xch[b][f][CT + c][lane] = acc[c];
+					if (!split_reverb) {
+						xch[b][f][c][lane] = x[c];
+					}
+					xch[b][f][kBusAt + c][lane] = acc[c];
 				}
 			}
 			__threadfence_block();
@@ -134,6 +147,7 @@ __global__ void __launch_bounds__(64) duo_kernel(const __grid_constant__ MixArgs
 		r0.end_state_only(a, 0, tile, lane);
 		r1.end_state_only(a, 1, tile, lane);
 		r2.end_state_only(a, 2, tile, lane);
+		r3in.end_state_only(a, 3, tile, lane);
 		store_passthrough_history<CT>(ss, 0, src, a, io_ok);
 		if (!F0::kIsNull) {
 			store_passthrough_history<CT>(ss, 1 + a.aux_index[0], src, a, io_ok);
@@ -145,7 +159,7 @@ __global__ void __launch_bounds__(64) duo_kernel(const __grid_constant__ MixArgs
 			store_passthrough_history<CT>(ss, 1 + a.aux_index[2], src, a, io_ok);
 		}
 	} else {
-		SlotRunner<CT, false, F3> r3;
+		SlotRunner<CT, false, Back3> r3;
 		r3.begin(a, 3, tile, lane, back_has_window ? window + lane : nullptr);
 		bar_arrive(kBarEmpty + 0);
 		bar_arrive(kBarEmpty + 1);
@@ -159,10 +173,14 @@ __global__ void __launch_bounds__(64) duo_kernel(const __grid_constant__ MixArgs
 				float x[CT], acc[CT];
 #pragma unroll
 				for (int c = 0; c < CT; ++c) {
-					x[c] = xch[b][f][c][lane];
-					acc[c] = xch[b][f][CT + c][lane];
+					x[c] = split_reverb ? 0.0F : xch[b][f][c][lane];
+					acc[c] = xch[b][f][kBusAt + c][lane];
 				}
-				r3.step(a, 3, x, acc);
+				if (split_reverb) {
+					r3.fx.template step<CT, true>(a.slot[3], x, acc, CT); // the tail does not read the wet bus
+				} else {
+					r3.step(a, 3, x, acc);
+				}
 				if (io_ok) {
 #pragma unroll
 					for (int c = 0; c < CT; ++c) {

@@ -30,7 +30,35 @@ constexpr int kPfDepth = kPfSlots - 1;      // samples in flight beyond the curr
 constexpr int kPfTaps = 24;
 constexpr int kPfWarpFloats = kPfSlots * kPfTaps * kLanes; // 12 KiB per reverb warp
 
-struct FxReverb {
+// Input stage of the reverb, shared by the whole effect (FxReverbT<true>) and by FxReverbInput,
+// which lets another warp run it ahead of the rest (duo.cuh): B-format -> A-format (mix_row with
+// the b2a matrix, oalsfxpp.cpp:6099-6113, 6377-6383), the master shelf filter(s), and the feed of the
+// main delay line (oalsfxpp.cpp:7821-7832 / 7867-7879).
+OALSFX_HD void reverb_input_stage(const ReverbCoef& c, const float* wet, BiquadHist* lp, BiquadHist* hp,
+	const LaneMem& ring, int pos)
+{
+	const int main_len = c.mask[0] + 1, main0 = c.ring_base[0], main_mask = c.mask[0];
+	constexpr float q = 0.288675134595F;
+	const float sgn[4][4] = {{q, q, q, q}, {q, -q, -q, q}, {q, q, -q, -q}, {q, -q, q, -q}};
+	OALSFX_UNROLL
+	for (int l = 0; l < 4; ++l) {
+		float a = 0.0F;
+		OALSFX_UNROLL
+		for (int k = 0; k < 4; ++k) {
+			a += wet[k] * sgn[l][k];
+		}
+		float v = biquad_step(c.lp, lp[l], a);
+		if (c.is_eax) {
+			v = biquad_step(c.hp, hp[l], v);
+		}
+		ring.st(main0 + l * main_len + (pos & main_mask), v);
+	}
+}
+
+// INPUT = false: the input stage (and the lp/hp filter history words of the state) belong to a
+// FxReverbInput running in another warp; `wet` is not read.
+template <bool INPUT>
+struct FxReverbT {
 	// Layout of the slot state in HBM (words, per lane).  Only the hot part lives in registers.
 	struct State {
 		BiquadHist lp[4], hp[4];
@@ -85,8 +113,10 @@ struct FxReverb {
 		ring.p = ring_p;
 		OALSFX_UNROLL
 		for (int l = 0; l < 4; ++l) {
-			load_words(lp[l], st + (kWLp + l * 4) * kLanes);
-			load_words(hp[l], st + (kWHp + l * 4) * kLanes);
+			if (INPUT) {
+				load_words(lp[l], st + (kWLp + l * 4) * kLanes);
+				load_words(hp[l], st + (kWHp + l * 4) * kLanes);
+			}
 			t60[l][0][0] = word_as_float(st[(kWT60 + l * 4 + 0) * kLanes]);
 			t60[l][0][1] = word_as_float(st[(kWT60 + l * 4 + 1) * kLanes]);
 			t60[l][1][0] = word_as_float(st[(kWT60 + l * 4 + 2) * kLanes]);
@@ -339,22 +369,8 @@ struct FxReverb {
 		const int eline_len = c.mask[2] + 1, eline0 = c.ring_base[2], eline_mask = c.mask[2];
 		const int lline_len = c.mask[4] + 1, lline0 = c.ring_base[4], lline_mask = c.mask[4];
 
-		// B-format -> A-format (mix_row with the b2a matrix, oalsfxpp.cpp:6099-6113, 6377-6383), the
-		// master shelf filter(s), and the feed of the main delay line (oalsfxpp.cpp:7821-7832 / 7867-7879).
-		constexpr float q = 0.288675134595F;
-		const float sgn[4][4] = {{q, q, q, q}, {q, -q, -q, q}, {q, q, -q, -q}, {q, -q, q, -q}};
-		OALSFX_UNROLL
-		for (int l = 0; l < 4; ++l) {
-			float a = 0.0F;
-			OALSFX_UNROLL
-			for (int k = 0; k < 4; ++k) {
-				a += wet[k] * sgn[l][k];
-			}
-			float v = biquad_step(c.lp, lp[l], a);
-			if (c.is_eax) {
-				v = biquad_step(c.hp, hp[l], v);
-			}
-			ring.st(main0 + l * main_len + (pos & main_mask), v);
+		if (INPUT) {
+			reverb_input_stage(c, wet, lp, hp, ring, pos);
 		}
 
 		float f[4];
@@ -483,8 +499,10 @@ struct FxReverb {
 	{
 		OALSFX_UNROLL
 		for (int l = 0; l < 4; ++l) {
-			store_words(lp[l], st + (kWLp + l * 4) * kLanes);
-			store_words(hp[l], st + (kWHp + l * 4) * kLanes);
+			if (INPUT) {
+				store_words(lp[l], st + (kWLp + l * 4) * kLanes);
+				store_words(hp[l], st + (kWHp + l * 4) * kLanes);
+			}
 			st[(kWT60 + l * 4 + 0) * kLanes] = float_as_word(t60[l][0][0]);
 			st[(kWT60 + l * 4 + 1) * kLanes] = float_as_word(t60[l][0][1]);
 			st[(kWT60 + l * 4 + 2) * kLanes] = float_as_word(t60[l][1][0]);
@@ -507,6 +525,50 @@ struct FxReverb {
 #if defined(__CUDA_ARCH__)
 		cp_async_wait_group<0>(); // nothing of this warp's window may still be in flight when the CTA exits
 #endif
+	}
+};
+
+using FxReverb = FxReverbT<true>;
+using FxReverbTail = FxReverbT<false>;
+
+// The reverb's input stage alone, for a warp that runs ahead of the FxReverbTail of the same slot.
+// Shares the slot's state region: owns the lp/hp history words, reads (never writes) the offset.
+struct FxReverbInput {
+	static constexpr bool kIsNull = false;
+	BiquadHist lp[4], hp[4];
+	int32_t offset;
+	LaneMem ring;
+
+	OALSFX_HD void set_prefetch(float*) {}
+	OALSFX_HD void prefetch_issue(const SlotCoef&, int) {}
+
+	template <int CT>
+	OALSFX_HD void begin(const SlotCoef&, uint32_t* st, float* ring_p, bool, int, int)
+	{
+		ring.p = ring_p;
+		OALSFX_UNROLL
+		for (int l = 0; l < 4; ++l) {
+			load_words(lp[l], st + (FxReverb::kWLp + l * 4) * kLanes);
+			load_words(hp[l], st + (FxReverb::kWHp + l * 4) * kLanes);
+		}
+		offset = static_cast<int32_t>(st[(FxReverb::kWScalars + 0) * kLanes]);
+	}
+
+	template <int CT, bool FAST = false>
+	OALSFX_HD void step(const SlotCoef& sc, const float* wet, float*, int)
+	{
+		reverb_input_stage(sc.u.reverb, wet, lp, hp, ring, offset);
+		offset += 1;
+	}
+
+	template <int CT>
+	OALSFX_HD void end_ct(const SlotCoef&, uint32_t* st, int)
+	{
+		OALSFX_UNROLL
+		for (int l = 0; l < 4; ++l) {
+			store_words(lp[l], st + (FxReverb::kWLp + l * 4) * kLanes);
+			store_words(hp[l], st + (FxReverb::kWHp + l * 4) * kLanes);
+		}
 	}
 };
 
