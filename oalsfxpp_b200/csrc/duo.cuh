@@ -25,6 +25,15 @@
 namespace oalsfx {
 namespace duo {
 
+#ifndef OALSFX_DUO_MIN_CTAS
+#define OALSFX_DUO_MIN_CTAS 6          // resident CTAs per SM the register allocation is sized for
+#endif
+
+#ifndef OALSFX_DUO_UNROLL
+#define OALSFX_DUO_UNROLL 1            // sample-loop unroll factor (2 lets ptxas rename the filter histories instead of moving them)
+#endif
+
+constexpr int kDuoUnroll = OALSFX_DUO_UNROLL;
 constexpr int kDuoChunk = 16;          // frames per hand-off
 constexpr int kBarFull = 1;            // named barriers 1,2: buffer b filled by the front warp
 constexpr int kBarEmpty = 3;           // named barriers 3,4: buffer b drained by the back warp
@@ -49,7 +58,7 @@ __device__ __forceinline__ void store_passthrough_history(uint32_t* ss, int send
 }
 
 template <int CT, class F0, class F1, class F2, class F3>
-__global__ void __launch_bounds__(64) duo_kernel(const __grid_constant__ MixArgs a)
+__global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(const __grid_constant__ MixArgs a)
 {
 	// A reverb in slot 3 is split: its input stage (B->A conversion, shelf filters, main-line feed,
 	// ~150 of its ~830 instructions per sample) runs in the front warp, which balances the two warps.
@@ -110,6 +119,7 @@ __global__ void __launch_bounds__(64) duo_kernel(const __grid_constant__ MixArgs
 			const int first = ci * kDuoChunk;
 			const int count = min(kDuoChunk, a.frames - first);
 			bar_sync(kBarEmpty + b);
+#pragma unroll (kDuoUnroll)
 			for (int f = 0; f < count; ++f) {
 				const int i = first + f;
 				float x[CT], acc[CT];
@@ -168,6 +178,7 @@ __global__ void __launch_bounds__(64) duo_kernel(const __grid_constant__ MixArgs
 			const int first = ci * kDuoChunk;
 			const int count = min(kDuoChunk, a.frames - first);
 			bar_sync(kBarFull + b);
+#pragma unroll (kDuoUnroll)
 			for (int f = 0; f < count; ++f) {
 				const int i = first + f;
 				float x[CT], acc[CT];

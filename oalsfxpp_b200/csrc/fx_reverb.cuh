@@ -38,14 +38,18 @@ OALSFX_HD void reverb_input_stage(const ReverbCoef& c, const float* wet, BiquadH
 	const LaneMem& ring, int pos)
 {
 	const int main_len = c.mask[0] + 1, main0 = c.ring_base[0], main_mask = c.mask[0];
+	// Every b2a entry is +-q, and w * (-q) == -(w * q) bit for bit, so the four products are formed
+	// once and added with the row's signs, in the reference's order k = 0..3 starting from 0.
 	constexpr float q = 0.288675134595F;
-	const float sgn[4][4] = {{q, q, q, q}, {q, -q, -q, q}, {q, q, -q, -q}, {q, -q, q, -q}};
+	const float p[4] = {wet[0] * q, wet[1] * q, wet[2] * q, wet[3] * q};
+	const bool neg[4][4] = {{false, false, false, false}, {false, true, true, false}, {false, false, true, true},
+		{false, true, false, true}};
 	OALSFX_UNROLL
 	for (int l = 0; l < 4; ++l) {
 		float a = 0.0F;
 		OALSFX_UNROLL
 		for (int k = 0; k < 4; ++k) {
-			a += wet[k] * sgn[l][k];
+			a = neg[l][k] ? a - p[k] : a + p[k];
 		}
 		float v = biquad_step(c.lp, lp[l], a);
 		if (c.is_eax) {

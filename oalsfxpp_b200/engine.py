@@ -32,6 +32,11 @@ class _Desc(C.Structure):
 
 
 def library_path():
+    """The in-tree CUDA library.  OALSFX_LIB may name another build of the SAME library (A/B kernel
+    tuning builds made by oalsfxpp_b200/csrc/Makefile with different -D flags); it is never a fallback."""
+    override = os.environ.get("OALSFX_LIB")
+    if override:
+        return os.path.abspath(override)
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "liboalsfx_b200.so")
 
 
