@@ -84,8 +84,8 @@ def cpu_baseline(target_seconds=12.0):
     if lib is None:
         return None
     threads = os.cpu_count() or 1
-    rate, _ = cpu_run(lib, threads, threads, 8)  # short probe to size the sample
     per_stream_blocks = 64
+    rate, _ = cpu_run(lib, threads, 2 * threads, per_stream_blocks)  # probe (same shape) to size the sample
     streams = max(threads, int(rate * target_seconds / (CHANNELS * BLOCK * per_stream_blocks)) // threads * threads)
     value, secs = cpu_run(lib, threads, streams, per_stream_blocks)
     return {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
@@ -102,8 +102,8 @@ def run_reference_arm(args):
         print(json.dumps({"impl": "reference", "unavailable": "no CPU checker library could be built"}))
         return 0
     threads = os.cpu_count() or 1
-    rate, _ = cpu_run(lib, threads, threads, 8)
     blocks = 32
+    rate, _ = cpu_run(lib, threads, 2 * threads, blocks)
     # each step: a bounded sample sized for ~2 s so K steps + W warm-ups stay within minutes
     streams = max(threads, int(rate * 2.0 / (CHANNELS * BLOCK * blocks)) // threads * threads)
     for _ in range(args.warmup):
@@ -280,7 +280,8 @@ def main():
         "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(S),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "mix_kernel<2,false,FxEqualizer,FxModDelay,FxEcho,FxReverb> (kChainStereo)",
+                     "traffic": traffic, "kernel": "duo_kernel<2,FxEqualizer,FxModDelay,FxEcho,FxReverb> (kDuoChainStereo): "
+                                                    "one launch = one step = the whole fused path",
                      "algorithmic_bytes_per_launch": BYTES_PER_FRAME * S * F, "kernel_ms_median": median_ms,
                      "peak_source": peak_src},
         "clocks": clocks.summary(),
