@@ -128,24 +128,55 @@ def run_reference_arm(args):
 
 # ---- clocks ----------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled every few ms WHILE the timed region runs (NVML; falls back
+    to the nvidia-smi query of B200_PROFILING.md when pynvml is unavailable)."""
     QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.samples, self._stop, self._thread = index, [], threading.Event(), None
+        self.index, self.sm, self.max_sm, self.reasons = index, [], None, set()
+        self._stop, self._thread, self._nvml = threading.Event(), None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self._handle, n.NVML_CLOCK_SM)))
+        bits = n.nvmlDeviceGetCurrentClocksEventReasons(self._handle)
+        for name, attr in (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
+                           ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+                           ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
+                           ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap")):
+            if bits & getattr(n, attr, 0):
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        parts = [p.strip() for p in out.strip().split(",")]
+        if len(parts) >= 6:
+            self.sm.append(float(parts[0]))
+            self.max_sm = float(parts[1])
+            for i, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
+                if parts[2 + i].lower().startswith("active"):
+                    self.reasons.add(name)
 
     def _loop(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.samples.append(parts)
+                if self._nvml:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.004 if self._nvml else 0.1)
 
     def __enter__(self):
         self._thread = threading.Thread(target=self._loop, daemon=True)
@@ -157,13 +188,11 @@ class ClockSampler:
         self._thread.join(timeout=10)
 
     def summary(self):
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(sm)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": ["no clock samples"]}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_sm, "reasons": sorted(self.reasons),
+                "samples": len(sm), "source": "nvml" if self._nvml else "nvidia-smi"}
 
 
 # ---- our arm ---------------------------------------------------------------------------------------
