@@ -41,6 +41,11 @@ public:
 	virtual bool reduce_bus(const float* data, long long ts, long long ls, long long fs, long long cs,
 		int num_streams, int frames, int channels, float* bus, void* stream) = 0;
 	virtual bool sync(void* stream) = 0;
+	// Engine-owned streams for overlapping host copies with kernels (host-buffer mix): create /
+	// destroy, and "everything enqueued on `signal` so far happens before what `waiter` gets next".
+	virtual void* stream_create() = 0;
+	virtual void stream_destroy(void* stream) = 0;
+	virtual bool stream_wait(void* waiter, void* signal) = 0;
 	virtual const std::string& error() const = 0;
 };
 

@@ -204,11 +204,54 @@ public:
 		return bind() && check(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)), "cudaStreamSynchronize");
 	}
 
+	void* stream_create() override
+	{
+		cudaStream_t s = nullptr;
+		if (!bind() || !check(cudaStreamCreate(&s), "cudaStreamCreate")) {
+			return nullptr;
+		}
+		return s;
+	}
+
+	void stream_destroy(void* stream) override
+	{
+		if (stream) {
+			cudaStreamDestroy(static_cast<cudaStream_t>(stream));
+		}
+	}
+
+	bool stream_wait(void* waiter, void* signal) override
+	{
+		if (!bind()) {
+			return false;
+		}
+		if (events_.empty()) {
+			events_.resize(64, nullptr);
+		}
+		cudaEvent_t& ev = events_[next_event_++ % events_.size()];
+		if (!ev && !check(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate")) {
+			return false;
+		}
+		return check(cudaEventRecord(ev, static_cast<cudaStream_t>(signal)), "cudaEventRecord") &&
+			check(cudaStreamWaitEvent(static_cast<cudaStream_t>(waiter), ev, 0), "cudaStreamWaitEvent");
+	}
+
+	~CudaBackend() override
+	{
+		for (cudaEvent_t ev : events_) {
+			if (ev) {
+				cudaEventDestroy(ev);
+			}
+		}
+	}
+
 	const std::string& error() const override { return error_; }
 
 private:
 	int device_;
 	std::string error_;
+	std::vector<cudaEvent_t> events_;
+	size_t next_event_ = 0;
 };
 
 } // namespace

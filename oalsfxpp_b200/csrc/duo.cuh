@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(const __gr
 	__shared__ float fwin[kFwWarpFloats];               // front warp: chorus/echo taps and input frames in flight
 	static_assert(4 + CT <= kFwTaps, "front window too small for this channel count");
 
-	const int tile = a.tiles ? static_cast<int>(a.tiles[blockIdx.x].tile) : static_cast<int>(blockIdx.x);
+	const int tile = a.tiles ? static_cast<int>(a.tiles[blockIdx.x].tile) : a.tile_first + static_cast<int>(blockIdx.x);
 	const int lane = threadIdx.x % kLanes;
 	const bool front = threadIdx.x < kLanes;
 	const bool io_ok = tile * kLanes + lane < a.num_streams;

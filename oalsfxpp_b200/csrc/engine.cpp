@@ -103,6 +103,12 @@ struct oalsfx_engine {
 	// Which fused kernel family serves whole-tile groups: 2 = duo (default), 1 = quad, 0 = the plain
 	// thread-per-stream twin.  OALSFX_KERNEL=duo|quad|single overrides (A/B measurements only).
 	int family = 2;
+	// Host-buffer mix: tile slice the next launches are restricted to (0 = all tiles), and the
+	// engine-owned streams that overlap H2D, kernels and D2H of consecutive slices.
+	int slice_first = 0, slice_count = 0;
+	void* pipe_in = nullptr;
+	void* pipe_run = nullptr;
+	void* pipe_out = nullptr;
 	std::string error;
 
 	~oalsfx_engine()
@@ -119,6 +125,9 @@ struct oalsfx_engine {
 		be->release(tile_list);
 		be->release(stage_in);
 		be->release(stage_out);
+		be->stream_destroy(pipe_in);
+		be->stream_destroy(pipe_run);
+		be->stream_destroy(pipe_out);
 		for (auto& kv : tables) {
 			be->release(kv.second);
 		}
@@ -409,6 +418,10 @@ struct oalsfx_engine {
 		a.dst = dst + frame0 * a.io_fs;
 		a.tiles = g.identity ? nullptr : tile_list + g.tile_begin;
 		a.tile_count = g.tile_count;
+		if (g.identity && slice_count > 0) { // host-buffer pipelining: only tiles [slice_first, +slice_count)
+			a.tile_first = slice_first;
+			a.tile_count = slice_count;
+		}
 		a.send_state = send_state;
 		const SendClass& sc = send_classes[static_cast<size_t>(g.key.send)];
 		a.direct = sc.direct_coef;
@@ -735,11 +748,57 @@ int oalsfx_engine_mix(oalsfx_engine* e, int frames, const float* src, float* dst
 				return e->fail(OALSFX_ERR_MEMORY, "Staging allocation failed: " + e->be->error());
 			}
 		}
+		dsrc = e->stage_in;
+		ddst = e->stage_out;
+		// One block, one group covering every tile (the common case): slice the tiles and overlap the
+		// upload of slice j+1, the kernel of slice j and the download of slice j-1 (PCIe is full duplex
+		// and the copies, not the kernel, bound this path).
+		if (e->groups_dirty && !e->rebuild_groups()) {
+			return e->fail(OALSFX_ERR_DEVICE, "Group table upload failed: " + e->be->error());
+		}
+		const int slices = std::min(e->tiles / 64, 16);
+		if (frames <= kMaxBlockFrames && e->groups.size() == 1 && e->groups[0].identity && slices >= 2 &&
+			layout == OALSFX_LAYOUT_STREAM_MAJOR) {
+			if (!e->pipe_in) {
+				e->pipe_in = e->be->stream_create();
+				e->pipe_run = e->be->stream_create();
+				e->pipe_out = e->be->stream_create();
+			}
+			if (e->pipe_in && e->pipe_run && e->pipe_out) {
+				if (!e->be->sync(cuda_stream)) {
+					return e->fail(OALSFX_ERR_DEVICE, e->be->error());
+				}
+				const Group g = e->groups[0];
+				const size_t per_tile = static_cast<size_t>(kLanes) * static_cast<size_t>(frames) * static_cast<size_t>(e->channels);
+				bool ok = true;
+				for (int j = 0; j < slices && ok; ++j) {
+					const int t0 = static_cast<int>(static_cast<long long>(e->tiles) * j / slices);
+					const int t1 = static_cast<int>(static_cast<long long>(e->tiles) * (j + 1) / slices);
+					const size_t first = per_tile * static_cast<size_t>(t0);
+					const size_t last = std::min(per_tile * static_cast<size_t>(t1), count);
+					ok = e->be->upload(e->stage_in + first, src + first, (last - first) * sizeof(float), e->pipe_in) &&
+						e->be->stream_wait(e->pipe_run, e->pipe_in);
+					e->slice_first = t0;
+					e->slice_count = t1 - t0;
+					ok = ok && e->launch_group(g, frames, dsrc, ddst, layout, frames, 0, true, e->pipe_run);
+					e->slice_first = e->slice_count = 0;
+					ok = ok && e->be->stream_wait(e->pipe_out, e->pipe_run) &&
+						e->be->download(dst + first, e->stage_out + first, (last - first) * sizeof(float), e->pipe_out);
+				}
+				ok = ok && e->be->sync(e->pipe_out) && e->be->sync(e->pipe_run);
+				if (!ok) {
+					return e->fail(OALSFX_ERR_DEVICE, e->be->error());
+				}
+				if (g.key.pending != 0) {
+					std::fill(e->pending.begin(), e->pending.end(), static_cast<uint8_t>(0));
+					e->groups_dirty = true;
+				}
+				return OALSFX_OK;
+			}
+		}
 		if (!e->be->upload(e->stage_in, src, count * sizeof(float), cuda_stream)) {
 			return e->fail(OALSFX_ERR_DEVICE, e->be->error());
 		}
-		dsrc = e->stage_in;
-		ddst = e->stage_out;
 	} else if (space != OALSFX_SPACE_DEVICE) {
 		return e->fail(OALSFX_ERR_ARGUMENT, "Unknown pointer space.");
 	}

@@ -42,6 +42,7 @@ struct MixArgs {
 	// Tiles covered by this launch: (tile index, lane mask); null = tiles 0..tile_count-1, all lanes.
 	const TileRef* tiles;
 	int32_t tile_count;
+	int32_t tile_first;                 // identity mapping only: first tile of this launch (host-buffer pipelining slices the tiles)
 	float* ring[kMaxSlots];          // per slot position: [tile][word][lane]
 	long long ring_tile_stride[kMaxSlots];
 	uint32_t* slot_state[kMaxSlots]; // per slot position: [tile][kSlotStateWords][lane]
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(64) mix_kernel(const __grid_constant__ MixArgs
 	if (warp >= a.tile_count) {
 		return;
 	}
-	int tile = warp;
+	int tile = a.tile_first + warp;
 	uint32_t mask = 0xFFFFFFFFU;
 	if (a.tiles) {
 		const TileRef t = a.tiles[warp];

@@ -808,7 +808,7 @@ template <int CT, template <int> class Q0, template <int> class Q1, template <in
 __global__ void __launch_bounds__(kQuadThreads, OALSFX_QUAD_MIN_CTAS) quad_kernel(const __grid_constant__ MixArgs a)
 {
 	__shared__ float pf_smem[kPfFloatsPerSlotUser]; // one prefetching slot user (the reverb) per kernel
-	const int tile = a.tiles ? static_cast<int>(a.tiles[blockIdx.x].tile) : static_cast<int>(blockIdx.x);
+	const int tile = a.tiles ? static_cast<int>(a.tiles[blockIdx.x].tile) : a.tile_first + static_cast<int>(blockIdx.x);
 	const int lane_in_tile = threadIdx.x >> 2;           // stream within the tile
 	const int j = threadIdx.x & 3;
 	const bool io_ok = tile * kLanes + lane_in_tile < a.num_streams;

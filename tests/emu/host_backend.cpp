@@ -52,7 +52,7 @@ public:
 			kernel_id = twin_of_quad(kernel_id);
 		}
 		for (int w = 0; w < a.tile_count; ++w) {
-			int tile = w;
+			int tile = a.tile_first + w;
 			uint32_t mask = 0xFFFFFFFFU;
 			if (a.tiles) {
 				tile = static_cast<int>(a.tiles[w].tile);
@@ -90,6 +90,9 @@ public:
 		return true;
 	}
 	bool sync(void*) override { return true; }
+	void* stream_create() override { return this; } // everything is synchronous here
+	void stream_destroy(void*) override {}
+	bool stream_wait(void*, void*) override { return true; }
 	const std::string& error() const override { return error_; }
 
 private:

@@ -135,3 +135,25 @@ def test_engine_argument_errors():
         with pytest.raises(ox.OalsfxError):
             eng.set_effect(0, T.echo, first_stream=3, n_streams=2)
         assert eng.mix(np.zeros((4, 0, 1), np.float32), frames=0).size == 0  # zero frames is a no-op
+
+
+def test_host_buffer_mix_is_sliced_without_changing_results(checker):
+    """>= 4096 streams in one uniform group: the host-buffer path uploads / mixes / downloads tile slices
+    on three overlapped streams (engine.cpp).  Results must not depend on the slicing, including the
+    ragged last tile and a parameter change (pending update) between blocks."""
+    lib = H.emu_lib()
+    S, block = 4100, 300
+    x = np.stack([H.noise(s % 7, 2, 2 * block) for s in range(S)])
+    with ox.Engine(S, F.stereo, 48000, 2, lib=lib) as eng:
+        eng.set_effect(0, T.echo)
+        eng.set_effect(1, T.eax_reverb)
+        y0 = eng.mix(np.ascontiguousarray(x[:, :block]))
+        eng.set_effect(1, T.eax_reverb, ox.default_props(T.eax_reverb, lib=lib, gain_=0.2, reflections_delay_=0.01))
+        y1 = eng.mix(np.ascontiguousarray(x[:, block:]))
+    y = np.concatenate([y0, y1], axis=1)
+    script = [("type", 0, T.echo), ("type", 1, T.eax_reverb), ("apply",), ("mix", block),
+              ("props", 1, ox.default_props(T.eax_reverb, lib=lib, gain_=0.2, reflections_delay_=0.01)), ("apply",),
+              ("mix", block)]
+    for s in (0, 1, 6, 2047, 2048, 4095, 4096, 4099):
+        expect = H.run_script_orc(checker, F.stereo, 48000, 2, script, x[s])
+        assert np.array_equal(expect, y[s]), s
