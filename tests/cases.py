@@ -122,6 +122,18 @@ def chain_cases(lib, frames=6000):
     yield ("chain-stereo-sine", F.stereo, 48000, 4, H.simple_script(chain, blocks), H.sine(7, 2, frames, 48000))
     yield ("chain-stereo-impulse", F.stereo, 48000, 4, H.simple_script(chain, blocks), H.impulse(2, frames))
     yield ("chain-stereo-burst", F.stereo, 48000, 4, H.simple_script(chain, blocks), H.burst(7, 2, frames, 600))
+    # the fused fast kernels' other paths: modulated reverb (no prefetch), tiny taps (direct reads), EAX off
+    for tag, rv_type, rv in (("underwater", T.eax_reverb, preset("Default", "underwater")),
+                             ("psychotic", T.eax_reverb, preset("Default", "psychotic")),
+                             ("tinytaps", T.eax_reverb, default(T.eax_reverb, density_=0.0, reflections_delay_=0.0,
+                                                                late_reverb_delay_=0.0)),
+                             ("std-reverb", T.reverb, preset("Default", "hangar"))):
+        slots = [(T.equalizer, default(T.equalizer, mid2_gain_=2.0)), (T.chorus, default(T.chorus, waveform_=0)),
+                 (T.echo, default(T.echo, delay_=0.0001, lr_delay_=0.0)), (rv_type, rv)]
+        yield (f"chain-stereo-{tag}", F.stereo, 48000, 4, H.simple_script(slots, blocks), H.noise(30, 2, frames))
+    yield ("chain-stereo-flanger", F.stereo, 48000, 4,
+           H.simple_script([(T.equalizer, None), (T.flanger, None), (T.echo, None), (T.eax_reverb, None)], blocks),
+           H.noise(31, 2, frames))
     yield ("chain-mono", F.mono, 48000, 4, H.simple_script(chain, blocks), H.noise(8, 1, frames))
     yield ("chain-5.1", F.five_point_one, 48000, 4, H.simple_script(chain, blocks), H.noise(9, 6, frames))
     yield ("chain2-mono96k", F.mono, 96000, 4, H.simple_script(chain2, blocks), H.noise(10, 1, frames))
