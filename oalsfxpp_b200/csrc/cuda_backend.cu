@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -178,7 +179,9 @@ public:
 			OALSFX_QUAD_TABLE(OALSFX_QX)
 #undef OALSFX_QX
 #define OALSFX_DX(id, CT, F0, F1, F2, F3, twin) \
-		case id: duo::duo_kernel<CT, F0, F1, F2, F3><<<static_cast<unsigned>(args.tile_count), 64, 0, st>>>(args); break;
+		case id: \
+			prefer_shared(id, duo::duo_kernel<CT, F0, F1, F2, F3>); \
+			duo::duo_kernel<CT, F0, F1, F2, F3><<<static_cast<unsigned>(args.tile_count), 64, tune_dyn_smem_, st>>>(args); break;
 			OALSFX_DUO_TABLE(OALSFX_DX)
 #undef OALSFX_DX
 		default:
@@ -186,6 +189,29 @@ public:
 			return false;
 		}
 		return check(cudaGetLastError(), kernel_name(kernel_id));
+	}
+
+	// The duo kernels stream through per-warp shared-memory windows (~29 KB per CTA) and have no use
+	// for L1: ask for the largest shared-memory carve-out so residency is register-limited (6 CTAs
+	// per SM) instead of stopping at the driver's default split (ncu: launch__occupancy_limit_shared_mem).
+	template <class K> void prefer_shared(int id, K kernel)
+	{
+		if (!carveout_done_[id]) {
+			// tuning knobs (experiments only): OALSFX_TUNE_CARVEOUT = percent or -1 (driver default),
+			// OALSFX_TUNE_DYN_SMEM = bytes of unused dynamic shared memory per CTA (caps residency)
+			int carveout = cudaSharedmemCarveoutMaxShared;
+			if (const char* e = getenv("OALSFX_TUNE_CARVEOUT")) {
+				carveout = atoi(e);
+			}
+			if (const char* e = getenv("OALSFX_TUNE_DYN_SMEM")) {
+				tune_dyn_smem_ = static_cast<size_t>(atoi(e));
+				cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tune_dyn_smem_));
+			}
+			if (carveout >= 0) {
+				cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+			}
+			carveout_done_[id] = true;
+		}
 	}
 
 	bool reduce_bus(const float* data, long long ts, long long ls, long long fs, long long cs,
@@ -252,6 +278,8 @@ private:
 	std::string error_;
 	std::vector<cudaEvent_t> events_;
 	size_t next_event_ = 0;
+	bool carveout_done_[kKernelEnd] = {};
+	size_t tune_dyn_smem_ = 0;
 };
 
 } // namespace

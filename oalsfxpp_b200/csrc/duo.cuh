@@ -35,11 +35,29 @@ namespace duo {
 
 constexpr int kDuoUnroll = OALSFX_DUO_UNROLL;
 constexpr int kDuoChunk = 16;          // frames per hand-off
-constexpr int kBarFull = 1;            // named barriers 1,2: buffer b filled by the front warp
-constexpr int kBarEmpty = 3;           // named barriers 3,4: buffer b drained by the back warp
+constexpr int kBarFull = 0;            // named barriers 0,1: buffer b filled by the front warp
+constexpr int kBarEmpty = 2;           // named barriers 2,3: buffer b drained by the back warp
 
-__device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-__device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+// The barrier id must be an immediate: with a register operand ptxas reserves all 16 hardware
+// barriers for the CTA, which caps residency at 4 CTAs per SM (ncu: launch__occupancy_limit_barriers).
+template <int ID> __device__ __forceinline__ void bar_sync_imm() { asm volatile("bar.sync %0, 64;" ::"n"(ID) : "memory"); }
+template <int ID> __device__ __forceinline__ void bar_arrive_imm() { asm volatile("bar.arrive %0, 64;" ::"n"(ID) : "memory"); }
+template <int BASE> __device__ __forceinline__ void bar_sync(int b)
+{
+	if (b) {
+		bar_sync_imm<BASE + 1>();
+	} else {
+		bar_sync_imm<BASE>();
+	}
+}
+template <int BASE> __device__ __forceinline__ void bar_arrive(int b)
+{
+	if (b) {
+		bar_arrive_imm<BASE + 1>();
+	} else {
+		bar_arrive_imm<BASE>();
+	}
+}
 
 template <int CT>
 __device__ __forceinline__ void store_passthrough_history(uint32_t* ss, int send, const float* src, const MixArgs& a, bool io_ok)
@@ -58,7 +76,12 @@ __device__ __forceinline__ void store_passthrough_history(uint32_t* ss, int send
 }
 
 template <int CT, class F0, class F1, class F2, class F3>
-__global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(const __grid_constant__ MixArgs a)
+#ifdef OALSFX_DUO_MAXNREG
+__global__ void __maxnreg__(OALSFX_DUO_MAXNREG) duo_kernel(
+#else
+__global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(
+#endif
+	const __grid_constant__ MixArgs a)
 {
 	// A reverb in slot 3 is split: its input stage (B->A conversion, shelf filters, main-line feed,
 	// ~150 of its ~830 instructions per sample) runs in the front warp, which balances the two warps.
@@ -68,7 +91,7 @@ __global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(const __gr
 	constexpr bool split_reverb = back_has_window;
 	using Front3 = typename std::conditional<split_reverb, FxReverbInput, FxNull>::type;
 	using Back3 = typename std::conditional<split_reverb, FxReverbTail, F3>::type;
-	__shared__ float window[back_has_window ? kPfWarpFloats : 1];
+	__shared__ __align__(16) float window[back_has_window ? kPfWarpFloats : 1];
 	constexpr int kBusAt = split_reverb ? 0 : CT;       // the input frame is only carried when the back warp needs it
 	__shared__ float xch[2][kDuoChunk][kBusAt + CT][kLanes]; // [buffer][frame][(x_0..x_C-1,) bus_0..bus_C-1][lane]
 	__shared__ float fwin[kFwWarpFloats];               // front warp: chorus/echo taps and input frames in flight
@@ -118,7 +141,7 @@ __global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(const __gr
 			const int b = ci & 1;
 			const int first = ci * kDuoChunk;
 			const int count = min(kDuoChunk, a.frames - first);
-			bar_sync(kBarEmpty + b);
+			bar_sync<kBarEmpty>(b);
 #pragma unroll (kDuoUnroll)
 			for (int f = 0; f < count; ++f) {
 				const int i = first + f;
@@ -151,7 +174,7 @@ __global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(const __gr
 				}
 			}
 			__threadfence_block();
-			bar_arrive(kBarFull + b);
+			bar_arrive<kBarFull>(b);
 		}
 		cp_async_wait_group<0>();
 		r0.end_state_only(a, 0, tile, lane);
@@ -171,13 +194,13 @@ __global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(const __gr
 	} else {
 		SlotRunner<CT, false, Back3> r3;
 		r3.begin(a, 3, tile, lane, back_has_window ? window + lane : nullptr);
-		bar_arrive(kBarEmpty + 0);
-		bar_arrive(kBarEmpty + 1);
+		bar_arrive<kBarEmpty>(0);
+		bar_arrive<kBarEmpty>(1);
 		for (int ci = 0; ci < chunks; ++ci) {
 			const int b = ci & 1;
 			const int first = ci * kDuoChunk;
 			const int count = min(kDuoChunk, a.frames - first);
-			bar_sync(kBarFull + b);
+			bar_sync<kBarFull>(b);
 #pragma unroll (kDuoUnroll)
 			for (int f = 0; f < count; ++f) {
 				const int i = first + f;
@@ -200,7 +223,7 @@ __global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(const __gr
 				}
 			}
 			if (ci + 2 < chunks) {
-				bar_arrive(kBarEmpty + b); // nobody waits for the last two drains
+				bar_arrive<kBarEmpty>(b); // nobody waits for the last two drains
 			}
 		}
 		r3.end_state_only(a, 3, tile, lane);

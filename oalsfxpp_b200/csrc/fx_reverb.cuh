@@ -13,22 +13,27 @@
 //
 // Memory system (device build): the 24 ring reads of a sample are the only long-latency operations
 // of the path.  When every delay exceeds the prefetch depth and no cross-fade / modulation is
-// active (the steady state of every preset), the reads of sample n + kPfDepth are issued with
-// cp.async (LDGSTS) into a per-warp shared-memory window while sample n is computed, so HBM
-// latency is covered by kPfDepth samples of arithmetic and no registers are held by loads in
-// flight.  Otherwise (first 128 samples after a tap change, modulated presets, tiny delays) the
-// rings are read directly at the point of use.  Both paths read the same values.
+// active (the steady state of every preset), the reads are BATCHED: one 16-byte cp.async.cg per lane
+// moves, for one tap, four consecutive ring positions of the whole tile (a contiguous 512-byte
+// run: lane = position * 8 + stream quad) into a per-warp shared-memory window, one batch (4
+// samples x 24 taps) ahead of the arithmetic.  That is a quarter of the copy instructions and
+// address arithmetic of per-sample requests, longer DRAM bursts, no registers held by loads in
+// flight, and -- .cg bypasses L1 -- no L1 lines tied up as landing buffers.  Otherwise (first 128
+// samples after a tap change, modulated presets, tiny delays) the rings are read directly at the
+// point of use.  Both paths read the same values.
 #ifndef OALSFX_FX_REVERB_CUH
 #define OALSFX_FX_REVERB_CUH
 
 namespace oalsfx {
 
-// Prefetch window geometry: [slot][tap 0..23][lane]; taps = {early, early all-pass, early line,
-// late, late line, late all-pass} x 4 lines.
-constexpr int kPfSlots = 4;                 // power of two
-constexpr int kPfDepth = kPfSlots - 1;      // samples in flight beyond the current one
+// Prefetch window geometry: [ring position & 7][tap 0..23][lane]; taps = {early, early all-pass,
+// early line, late, late line, late all-pass} x 4 lines.  Two batches of kPfBatch positions: the one
+// being consumed and the one in flight.
+constexpr int kPfBatch = 4;                 // ring positions per batched copy (32 lanes x 16 B = 4 lines)
+constexpr int kPfSlots = 2 * kPfBatch;      // power of two
+constexpr int kPfDepth = kPfSlots - 1;      // furthest position requested beyond the current one
 constexpr int kPfTaps = 24;
-constexpr int kPfWarpFloats = kPfSlots * kPfTaps * kLanes; // 12 KiB per reverb warp
+constexpr int kPfWarpFloats = kPfSlots * kPfTaps * kLanes; // 24 KiB per reverb warp
 
 // Input stage of the reverb, shared by the whole effect (FxReverbT<true>) and by FxReverbInput,
 // which lets another warp run it ahead of the rest (duo.cuh): B-format -> A-format (mix_row with
@@ -97,7 +102,6 @@ struct FxReverbT {
 	// prefetch pipeline (device build; pf_col == nullptr disables it)
 	float* pf_col;
 	const float* pf_cur;
-	int32_t pos_issue;
 	bool primed, can_pf;
 	bool pan_static;   // this sub-chunk: no gain ramps and every one of the 8 x C pan gains is audible
 
@@ -165,9 +169,15 @@ struct FxReverbT {
 		fade = static_cast<float>(fade_count) / kFadeSamples;
 		faded = false;
 		pf_cur = nullptr;
-		pos_issue = 0;
 		primed = false;
 		can_pf = false;
+#if defined(__CUDA_ARCH__)
+		// A window is only handed to whole tiles (all 32 lanes running); the batches also need every
+		// stream of the tile at the same ring position (streams created together, the normal case).
+		if (pf_col != nullptr && !__all_sync(0xFFFFFFFFU, offset == __shfl_sync(0xFFFFFFFFU, offset, 0))) {
+			pf_col = nullptr;
+		}
+#endif
 	}
 
 	// Sub-chunk prologue: size (oalsfxpp.cpp:6088-6096) and pan-gain stepping (MixHelpers::mix,
@@ -311,19 +321,25 @@ struct FxReverbT {
 	}
 
 #if defined(__CUDA_ARCH__)
-	// Issue the 24 reads of ring position p into window slot p % kPfSlots.
-	__device__ __forceinline__ void issue_reads(const ReverbCoef& c, int p) const
+	// Request ring positions p4 .. p4+3 (p4 a multiple of kPfBatch) of all 24 taps: lane = s * 8 + q
+	// copies streams 4q .. 4q+3 of position p4 + s, i.e. the warp moves one contiguous 512-byte run
+	// per tap (the rings are line-major: consecutive positions of a line are consecutive 128-byte rows).
+	__device__ __forceinline__ void issue_batch(const ReverbCoef& c, int p4) const
 	{
-		float* slot = pf_col + (p & (kPfSlots - 1)) * (kPfTaps * kLanes);
+		const int lane = threadIdx.x % kLanes;
+		const int q4 = (lane & 7) * 4;
+		const int ps = p4 + (lane >> 3);
+		float* dst = pf_col - lane + (ps & (kPfSlots - 1)) * (kPfTaps * kLanes) + q4;
+		const float* src = ring.p - lane + q4;
 		const int len0 = c.mask[0] + 1, len1 = c.mask[1] + 1, len2 = c.mask[2] + 1, len3 = c.mask[3] + 1, len4 = c.mask[4] + 1;
 #pragma unroll
 		for (int l = 0; l < 4; ++l) {
-			cp_async_f32(slot + (0 + l) * kLanes, ring.p + static_cast<unsigned>(c.ring_base[0] + l * len0 + ((p - c.early_tap[l]) & c.mask[0])) * kLanes);
-			cp_async_f32(slot + (4 + l) * kLanes, ring.p + static_cast<unsigned>(c.ring_base[1] + l * len1 + ((p - c.early_ap_off[l]) & c.mask[1])) * kLanes);
-			cp_async_f32(slot + (8 + l) * kLanes, ring.p + static_cast<unsigned>(c.ring_base[2] + l * len2 + ((p - c.early_off[l]) & c.mask[2])) * kLanes);
-			cp_async_f32(slot + (12 + l) * kLanes, ring.p + static_cast<unsigned>(c.ring_base[0] + l * len0 + ((p - c.late_tap[l]) & c.mask[0])) * kLanes);
-			cp_async_f32(slot + (16 + l) * kLanes, ring.p + static_cast<unsigned>(c.ring_base[4] + l * len4 + ((p - c.late_off[l]) & c.mask[4])) * kLanes);
-			cp_async_f32(slot + (20 + l) * kLanes, ring.p + static_cast<unsigned>(c.ring_base[3] + l * len3 + ((p - c.late_ap_off[l]) & c.mask[3])) * kLanes);
+			cp_async_16(dst + (0 + l) * kLanes, src + static_cast<unsigned>(c.ring_base[0] + l * len0 + ((ps - c.early_tap[l]) & c.mask[0])) * kLanes);
+			cp_async_16(dst + (4 + l) * kLanes, src + static_cast<unsigned>(c.ring_base[1] + l * len1 + ((ps - c.early_ap_off[l]) & c.mask[1])) * kLanes);
+			cp_async_16(dst + (8 + l) * kLanes, src + static_cast<unsigned>(c.ring_base[2] + l * len2 + ((ps - c.early_off[l]) & c.mask[2])) * kLanes);
+			cp_async_16(dst + (12 + l) * kLanes, src + static_cast<unsigned>(c.ring_base[0] + l * len0 + ((ps - c.late_tap[l]) & c.mask[0])) * kLanes);
+			cp_async_16(dst + (16 + l) * kLanes, src + static_cast<unsigned>(c.ring_base[4] + l * len4 + ((ps - c.late_off[l]) & c.mask[4])) * kLanes);
+			cp_async_16(dst + (20 + l) * kLanes, src + static_cast<unsigned>(c.ring_base[3] + l * len3 + ((ps - c.late_ap_off[l]) & c.mask[3])) * kLanes);
 		}
 		cp_async_commit_group();
 	}
@@ -338,16 +354,23 @@ struct FxReverbT {
 		}
 		const int pos = offset;
 #if defined(__CUDA_ARCH__)
-		if (can_pf) {
-			if (!primed) {
-				pos_issue = pos;
-				primed = true;
+		// The batched copies are a whole-warp affair (a lane fetches other lanes' streams), so the
+		// decision is a vote: every lane of the tile must be in the prefetchable state.
+		if (pf_col != nullptr && __all_sync(0xFFFFFFFFU, can_pf)) {
+			// Invariant while primed: the batch holding `pos` and the one after it have been requested.
+			const bool batch_start = (pos & (kPfBatch - 1)) == 0;
+			if (!primed || batch_start) {
+				__syncwarp(); // every lane is done with the window rows about to be overwritten
+				if (!primed) {
+					issue_batch(c, pos & ~(kPfBatch - 1));
+					issue_batch(c, (pos & ~(kPfBatch - 1)) + kPfBatch);
+					primed = true;
+				} else {
+					issue_batch(c, pos + kPfBatch);
+				}
+				cp_async_wait_group<1>(); // all but the newest batch: the one holding `pos` has landed
+				__syncwarp();             // ... for every lane's share of it
 			}
-			while (pos_issue - pos <= kPfDepth) {
-				issue_reads(c, pos_issue);
-				pos_issue += 1;
-			}
-			cp_async_wait_group<kPfDepth>();
 			pf_cur = pf_col + (pos & (kPfSlots - 1)) * (kPfTaps * kLanes);
 			body<CT, true>(c, wet, acc, channels, pos); // branch-free: every read is a shared-memory load
 		} else {

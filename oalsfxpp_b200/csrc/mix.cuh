@@ -271,7 +271,7 @@ template <int CT, bool SF, class F0, class F1, class F2, class F3>
 __global__ void __launch_bounds__(64) mix_kernel(const __grid_constant__ MixArgs a)
 {
 	constexpr bool has_window = PrefetchUser<F0, F1, F2, F3>::value >= 0;
-	__shared__ float window[has_window ? (64 / kLanes) * kPfWarpFloats : 1];
+	__shared__ __align__(16) float window[has_window ? (64 / kLanes) * kPfWarpFloats : 1];
 	const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / kLanes;
 	const int lane = threadIdx.x % kLanes;
 	if (warp >= a.tile_count) {
@@ -287,7 +287,10 @@ __global__ void __launch_bounds__(64) mix_kernel(const __grid_constant__ MixArgs
 	if (!((mask >> lane) & 1U) || tile * kLanes + lane >= a.num_streams) {
 		return;
 	}
-	mix_stream<CT, SF, F0, F1, F2, F3>(a, tile, lane, has_window ? window + (threadIdx.x / kLanes) * kPfWarpFloats + lane : nullptr);
+	// The reverb's batched prefetch is a whole-warp operation: only complete tiles get a window.
+	const bool whole_tile = mask == 0xFFFFFFFFU && (tile + 1) * kLanes <= a.num_streams;
+	mix_stream<CT, SF, F0, F1, F2, F3>(a, tile, lane,
+		has_window && whole_tile ? window + (threadIdx.x / kLanes) * kPfWarpFloats + lane : nullptr);
 }
 #endif
 
