@@ -39,29 +39,47 @@ constexpr int kPfWarpFloats = kPfSlots * kPfTaps * kLanes; // 24 KiB per reverb 
 // which lets another warp run it ahead of the rest (duo.cuh): B-format -> A-format (mix_row with
 // the b2a matrix, oalsfxpp.cpp:6099-6113, 6377-6383), the master shelf filter(s), and the feed of the
 // main delay line (oalsfxpp.cpp:7821-7832 / 7867-7879).
+OALSFX_HD F2 biquad_step2(const Biquad& c, BiquadHist& ha, BiquadHist& hb, F2 x)
+{
+	// Two filters with the same coefficients (FilterState::process, oalsfxpp.cpp:984-1036), one per half.
+	const F2 x0 = f2(ha.x0, hb.x0), x1 = f2(ha.x1, hb.x1), y0 = f2(ha.y0, hb.y0), y1 = f2(ha.y1, hb.y1);
+	const F2 y = (x * c.b0) + (x0 * c.b1) + (x1 * c.b2) - (y0 * c.a1) - (y1 * c.a2);
+	ha.x1 = ha.x0;
+	hb.x1 = hb.x0;
+	ha.x0 = f2_lo(x);
+	hb.x0 = f2_hi(x);
+	ha.y1 = ha.y0;
+	hb.y1 = hb.y0;
+	ha.y0 = f2_lo(y);
+	hb.y0 = f2_hi(y);
+	return y;
+}
+
 OALSFX_HD void reverb_input_stage(const ReverbCoef& c, const float* wet, BiquadHist* lp, BiquadHist* hp,
 	const LaneMem& ring, int pos)
 {
 	const int main_len = c.mask[0] + 1, main0 = c.ring_base[0], main_mask = c.mask[0];
 	// Every b2a entry is +-q, and w * (-q) == -(w * q) bit for bit, so the four products are formed
-	// once and added with the row's signs, in the reference's order k = 0..3 starting from 0.
+	// once and added with the row's signs, in the reference's order k = 0..3 starting from 0:
+	//   line 0: + + + +    line 1: + - - +    line 2: + + - -    line 3: + - + -
+	// Lines (0,1) and (2,3) are computed as pairs; a row's +-p_k is the matching half of (p_k, -p_k).
 	constexpr float q = 0.288675134595F;
-	const float p[4] = {wet[0] * q, wet[1] * q, wet[2] * q, wet[3] * q};
-	const bool neg[4][4] = {{false, false, false, false}, {false, true, true, false}, {false, false, true, true},
-		{false, true, false, true}};
-	OALSFX_UNROLL
-	for (int l = 0; l < 4; ++l) {
-		float a = 0.0F;
-		OALSFX_UNROLL
-		for (int k = 0; k < 4; ++k) {
-			a = neg[l][k] ? a - p[k] : a + p[k];
-		}
-		float v = biquad_step(c.lp, lp[l], a);
-		if (c.is_eax) {
-			v = biquad_step(c.hp, hp[l], v);
-		}
-		ring.st(main0 + l * main_len + (pos & main_mask), v);
+	const F2 zero = f2(0.0F, 0.0F);
+	const F2 p0 = f2_bcast(wet[0] * q), p3 = f2_bcast(wet[3] * q);
+	const F2 p1 = f2_bcast(wet[1]) * f2(q, -q);   // (+p1, -p1)
+	const F2 p2 = f2_bcast(wet[2]) * f2(q, -q);   // (+p2, -p2)
+	F2 a01 = (((zero + p0) + p1) + p2) + p3;      // (p0+p1+p2+p3, p0-p1-p2+p3)
+	F2 a23 = (((zero + p0) + p1) - p2) - p3;      // (p0+p1-p2-p3, p0-p1+p2-p3)
+	a01 = biquad_step2(c.lp, lp[0], lp[1], a01);
+	a23 = biquad_step2(c.lp, lp[2], lp[3], a23);
+	if (c.is_eax) {
+		a01 = biquad_step2(c.hp, hp[0], hp[1], a01);
+		a23 = biquad_step2(c.hp, hp[2], hp[3], a23);
 	}
+	ring.st(main0 + 0 * main_len + (pos & main_mask), f2_lo(a01));
+	ring.st(main0 + 1 * main_len + (pos & main_mask), f2_hi(a01));
+	ring.st(main0 + 2 * main_len + (pos & main_mask), f2_lo(a23));
+	ring.st(main0 + 3 * main_len + (pos & main_mask), f2_hi(a23));
 }
 
 // INPUT = false: the input stage (and the lp/hp filter history words of the state) belong to a
@@ -87,7 +105,7 @@ struct FxReverbT {
 
 	// hot state
 	BiquadHist lp[4], hp[4];
-	float t60[4][2][2];
+	F2 t60p[2][2][2];            // late T60 filter states of lines (2h, 2h+1): [h][section][x1 / y1]
 	float cur_gain[8][kMaxChannels];
 	int32_t offset, fade_count, mod_index, mod_range;
 	float mod_filter;
@@ -125,10 +143,14 @@ struct FxReverbT {
 				load_words(lp[l], st + (kWLp + l * 4) * kLanes);
 				load_words(hp[l], st + (kWHp + l * 4) * kLanes);
 			}
-			t60[l][0][0] = word_as_float(st[(kWT60 + l * 4 + 0) * kLanes]);
-			t60[l][0][1] = word_as_float(st[(kWT60 + l * 4 + 1) * kLanes]);
-			t60[l][1][0] = word_as_float(st[(kWT60 + l * 4 + 2) * kLanes]);
-			t60[l][1][1] = word_as_float(st[(kWT60 + l * 4 + 3) * kLanes]);
+		}
+		OALSFX_UNROLL
+		for (int h = 0; h < 2; ++h) {
+			OALSFX_UNROLL
+			for (int w = 0; w < 4; ++w) {
+				t60p[h][w >> 1][w & 1] = f2(word_as_float(st[(kWT60 + (2 * h) * 4 + w) * kLanes]),
+					word_as_float(st[(kWT60 + (2 * h + 1) * 4 + w) * kLanes]));
+			}
 		}
 		OALSFX_UNROLL
 		for (int l = 0; l < 8; ++l) {
@@ -291,33 +313,52 @@ struct FxReverbT {
 		return a + ((b - a) * mu);
 	}
 
-	OALSFX_HD static void scatter(float* v, float x, float y)
+	// vector_partial_scatter (oalsfxpp.cpp:7510-7521) on lines held as pairs a = (f0, f1), b = (f2, f3):
+	//   v0 = x*f0 + y*(f1 + -f2 + f3)    v1 = x*f1 + y*(-f0 + f2 + f3)
+	//   v2 = x*f2 + y*(f0 + -f1 + f3)    v3 = x*f3 + y*(-f0 + -f1 + -f2)
+	// The four inner sums mix the halves, so they stay scalar; the products and the outer sums are packed.
+	OALSFX_HD static void scatter2(F2& a, F2& b, float x, float y)
 	{
-		const float f0 = v[0], f1 = v[1], f2 = v[2], f3 = v[3];
-		v[0] = (x * f0) + (y * (f1 + -f2 + f3));
-		v[1] = (x * f1) + (y * (-f0 + f2 + f3));
-		v[2] = (x * f2) + (y * (f0 + -f1 + f3));
-		v[3] = (x * f3) + (y * (-f0 + -f1 + -f2));
+		const float f0 = f2_lo(a), f1 = f2_hi(a), f2v = f2_lo(b), f3 = f2_hi(b);
+		const float i0 = (f1 + -f2v) + f3, i1 = (-f0 + f2v) + f3, i2 = (f0 + -f1) + f3, i3 = (-f0 + -f1) + -f2v;
+		a = (a * x) + (f2(i0, i1) * y);
+		b = (b * x) + (f2(i2, i3) * y);
 	}
 
+	// The same scatter applied to the REVERSED vector r = (f3, f2, f1, f0) (vector_reverse,
+	// oalsfxpp.cpp:7652, 7781), returned reversed as well -- a = (v3, v2), b = (v1, v0) -- so that no half
+	// ever has to change sides:  v0 = x*f3 + y*(f2 + -f1 + f0)   v1 = x*f2 + y*(-f3 + f1 + f0)
+	//                            v2 = x*f1 + y*(f3 + -f2 + f0)   v3 = x*f0 + y*(-f3 + -f2 + -f1)
+	OALSFX_HD static void scatter2_reversed(F2& a, F2& b, float x, float y)
+	{
+		const float f0 = f2_lo(a), f1 = f2_hi(a), f2v = f2_lo(b), f3 = f2_hi(b);
+		const float i0 = (f2v + -f1) + f0, i1 = (-f3 + f1) + f0, i2 = (f3 + -f2v) + f0, i3 = (-f3 + -f2v) + -f1;
+		a = (a * x) + (f2(i3, i2) * y);
+		b = (b * x) + (f2(i1, i0) * y);
+	}
+
+	// vector_allpass_x (oalsfxpp.cpp:7533-7562) on line pairs.
 	template <bool PF>
-	OALSFX_HD void vector_allpass(const ReverbCoef& c, float* vec, int ring_idx, int tap_base, int group,
+	OALSFX_HD void vector_allpass2(const ReverbCoef& c, F2& va, F2& vb, int ring_idx, int tap_base, int group,
 		const int32_t* new_off, int pos, float mu) const
 	{
 		const int len = c.mask[ring_idx] + 1;
 		const int word0 = c.ring_base[ring_idx];
-		float f[4];
-		OALSFX_UNROLL
-		for (int i = 0; i < 4; ++i) {
-			const float input = vec[i];
-			vec[i] = tap<PF>(tap_base + i, word0 + i * len, c.mask[ring_idx], pos, group, i, new_off[i], mu) - (c.ap_feed_coeff * input);
-			f[i] = input + (c.ap_feed_coeff * vec[i]);
-		}
-		scatter(f, c.mix_x, c.mix_y);
-		OALSFX_UNROLL
-		for (int i = 0; i < 4; ++i) {
-			ring.st(word0 + i * len + (pos & c.mask[ring_idx]), f[i]);
-		}
+		const int mask = c.mask[ring_idx];
+		const F2 ta = f2(tap<PF>(tap_base + 0, word0 + 0 * len, mask, pos, group, 0, new_off[0], mu),
+			tap<PF>(tap_base + 1, word0 + 1 * len, mask, pos, group, 1, new_off[1], mu));
+		const F2 tb = f2(tap<PF>(tap_base + 2, word0 + 2 * len, mask, pos, group, 2, new_off[2], mu),
+			tap<PF>(tap_base + 3, word0 + 3 * len, mask, pos, group, 3, new_off[3], mu));
+		const F2 ina = va, inb = vb;
+		va = ta - (ina * c.ap_feed_coeff);
+		vb = tb - (inb * c.ap_feed_coeff);
+		F2 fa = ina + (va * c.ap_feed_coeff);
+		F2 fb = inb + (vb * c.ap_feed_coeff);
+		scatter2(fa, fb, c.mix_x, c.mix_y);
+		ring.st(word0 + 0 * len + (pos & mask), f2_lo(fa));
+		ring.st(word0 + 1 * len + (pos & mask), f2_hi(fa));
+		ring.st(word0 + 2 * len + (pos & mask), f2_lo(fb));
+		ring.st(word0 + 3 * len + (pos & mask), f2_hi(fb));
 	}
 
 #if defined(__CUDA_ARCH__)
@@ -400,31 +441,38 @@ struct FxReverbT {
 			reverb_input_stage(c, wet, lp, hp, ring, pos);
 		}
 
-		float f[4];
+		// The four lines are carried as two pairs: a = lines (0, 1), b = lines (2, 3).
+		F2 fa, fb;
 		float early_out[4], late_out[4];
 
 		// ---- early reflections (oalsfxpp.cpp:7625-7672) ----
-		OALSFX_UNROLL
-		for (int j = 0; j < 4; ++j) {
-			f[j] = tap<PF>(0 + j, main0 + j * main_len, main_mask, pos, 0, j, c.early_tap[j], mu) * c.early_tap_coeff[j];
-		}
-		vector_allpass<PF>(c, f, 1, 4, 1, c.early_ap_off, pos, mu);
-		OALSFX_UNROLL
-		for (int j = 0; j < 4; ++j) {
-			ring.st(eline0 + j * eline_len + (pos & eline_mask), f[3 - j]); // delay_line_in4_rev
-		}
-		OALSFX_UNROLL
-		for (int j = 0; j < 4; ++j) {
-			f[j] += tap<PF>(8 + j, eline0 + j * eline_len, eline_mask, pos, 2, j, c.early_off[j], mu) * c.early_coeff[j];
-			early_out[j] = f[j];
-		}
+		fa = f2(tap<PF>(0, main0 + 0 * main_len, main_mask, pos, 0, 0, c.early_tap[0], mu),
+			tap<PF>(1, main0 + 1 * main_len, main_mask, pos, 0, 1, c.early_tap[1], mu)) * f2(c.early_tap_coeff[0], c.early_tap_coeff[1]);
+		fb = f2(tap<PF>(2, main0 + 2 * main_len, main_mask, pos, 0, 2, c.early_tap[2], mu),
+			tap<PF>(3, main0 + 3 * main_len, main_mask, pos, 0, 3, c.early_tap[3], mu)) * f2(c.early_tap_coeff[2], c.early_tap_coeff[3]);
+		vector_allpass2<PF>(c, fa, fb, 1, 4, 1, c.early_ap_off, pos, mu);
+		// delay_line_in4_rev: line j receives f[3 - j]
+		ring.st(eline0 + 0 * eline_len + (pos & eline_mask), f2_hi(fb));
+		ring.st(eline0 + 1 * eline_len + (pos & eline_mask), f2_lo(fb));
+		ring.st(eline0 + 2 * eline_len + (pos & eline_mask), f2_hi(fa));
+		ring.st(eline0 + 3 * eline_len + (pos & eline_mask), f2_lo(fa));
+		fa = fa + (f2(tap<PF>(8, eline0 + 0 * eline_len, eline_mask, pos, 2, 0, c.early_off[0], mu),
+			tap<PF>(9, eline0 + 1 * eline_len, eline_mask, pos, 2, 1, c.early_off[1], mu)) * f2(c.early_coeff[0], c.early_coeff[1]));
+		fb = fb + (f2(tap<PF>(10, eline0 + 2 * eline_len, eline_mask, pos, 2, 2, c.early_off[2], mu),
+			tap<PF>(11, eline0 + 3 * eline_len, eline_mask, pos, 2, 3, c.early_off[3], mu)) * f2(c.early_coeff[2], c.early_coeff[3]));
+		early_out[0] = f2_lo(fa);
+		early_out[1] = f2_hi(fa);
+		early_out[2] = f2_lo(fb);
+		early_out[3] = f2_hi(fb);
 		{
-			float r[4] = {f[3], f[2], f[1], f[0]}; // vector_reverse
-			scatter(r, c.mix_x, c.mix_y);
-			OALSFX_UNROLL
-			for (int j = 0; j < 4; ++j) {
-				ring.st(main0 + j * main_len + ((pos - c.late_feed_tap) & main_mask), r[j]);
-			}
+			// vector_reverse + scatter, fed to the late reverb through the main line
+			F2 ra = fa, rb = fb;
+			scatter2_reversed(ra, rb, c.mix_x, c.mix_y); // ra = (v3, v2), rb = (v1, v0)
+			const int feed = (pos - c.late_feed_tap) & main_mask;
+			ring.st(main0 + 0 * main_len + feed, f2_hi(rb));
+			ring.st(main0 + 1 * main_len + feed, f2_lo(rb));
+			ring.st(main0 + 2 * main_len + feed, f2_hi(ra));
+			ring.st(main0 + 3 * main_len + feed, f2_lo(ra));
 		}
 
 		// ---- late reverb (oalsfxpp.cpp:7735-7794) ----
@@ -448,39 +496,47 @@ struct FxReverbT {
 				mod_delay = static_cast<int>(lroundf(mod_filter * sinus));
 			}
 		}
-		OALSFX_UNROLL
-		for (int j = 0; j < 4; ++j) {
-			f[j] = tap<PF>(12 + j, main0 + j * main_len, main_mask, pos, 3, j, c.late_tap[j], mu) * c.density_gain;
-		}
+		fa = f2(tap<PF>(12, main0 + 0 * main_len, main_mask, pos, 3, 0, c.late_tap[0], mu),
+			tap<PF>(13, main0 + 1 * main_len, main_mask, pos, 3, 1, c.late_tap[1], mu)) * c.density_gain;
+		fb = f2(tap<PF>(14, main0 + 2 * main_len, main_mask, pos, 3, 2, c.late_tap[2], mu),
+			tap<PF>(15, main0 + 3 * main_len, main_mask, pos, 3, 3, c.late_tap[3], mu)) * c.density_gain;
 		const int mod_pos = pos - mod_delay;
+		fa = fa + f2(tap<PF>(16, lline0 + 0 * lline_len, lline_mask, mod_pos, 5, 0, c.late_off[0], mu),
+			tap<PF>(17, lline0 + 1 * lline_len, lline_mask, mod_pos, 5, 1, c.late_off[1], mu));
+		fb = fb + f2(tap<PF>(18, lline0 + 2 * lline_len, lline_mask, mod_pos, 5, 2, c.late_off[2], mu),
+			tap<PF>(19, lline0 + 3 * lline_len, lline_mask, mod_pos, 5, 3, c.late_off[3], mu));
 		OALSFX_UNROLL
-		for (int j = 0; j < 4; ++j) {
-			f[j] += tap<PF>(16 + j, lline0 + j * lline_len, lline_mask, mod_pos, 5, j, c.late_off[j], mu);
-		}
-		OALSFX_UNROLL
-		for (int j = 0; j < 4; ++j) {
-			// late_t60_filter: two first-order sections and the mid gain (oalsfxpp.cpp:7691-7719)
-			const float in = f[j];
-			const float o1 = (c.t60_lf[j][0] * in) + (c.t60_lf[j][1] * t60[j][0][0]) + (c.t60_lf[j][2] * t60[j][0][1]);
-			t60[j][0][0] = in;
-			t60[j][0][1] = o1;
-			const float o2 = (c.t60_hf[j][0] * o1) + (c.t60_hf[j][1] * t60[j][1][0]) + (c.t60_hf[j][2] * t60[j][1][1]);
-			t60[j][1][0] = o1;
-			t60[j][1][1] = o2;
-			f[j] = c.t60_mid[j] * o2;
-		}
-		vector_allpass<PF>(c, f, 3, 20, 4, c.late_ap_off, pos, mu);
-		OALSFX_UNROLL
-		for (int j = 0; j < 4; ++j) {
-			late_out[j] = f[j];
-		}
-		{
-			float r[4] = {f[3], f[2], f[1], f[0]};
-			scatter(r, c.mix_x, c.mix_y);
-			OALSFX_UNROLL
-			for (int j = 0; j < 4; ++j) {
-				ring.st(lline0 + j * lline_len + (pos & lline_mask), r[j]);
+		for (int h = 0; h < 2; ++h) {
+			// late_t60_filter: two first-order sections and the mid gain (oalsfxpp.cpp:7691-7719), lines 2h, 2h+1
+			const int j = 2 * h;
+			const F2 in = (h == 0 ? fa : fb);
+			const F2 o1 = (f2(c.t60_lf[j][0], c.t60_lf[j + 1][0]) * in) + (f2(c.t60_lf[j][1], c.t60_lf[j + 1][1]) * t60p[h][0][0]) +
+				(f2(c.t60_lf[j][2], c.t60_lf[j + 1][2]) * t60p[h][0][1]);
+			t60p[h][0][0] = in;
+			t60p[h][0][1] = o1;
+			const F2 o2 = (f2(c.t60_hf[j][0], c.t60_hf[j + 1][0]) * o1) + (f2(c.t60_hf[j][1], c.t60_hf[j + 1][1]) * t60p[h][1][0]) +
+				(f2(c.t60_hf[j][2], c.t60_hf[j + 1][2]) * t60p[h][1][1]);
+			t60p[h][1][0] = o1;
+			t60p[h][1][1] = o2;
+			const F2 out = f2(c.t60_mid[j], c.t60_mid[j + 1]) * o2;
+			if (h == 0) {
+				fa = out;
+			} else {
+				fb = out;
 			}
+		}
+		vector_allpass2<PF>(c, fa, fb, 3, 20, 4, c.late_ap_off, pos, mu);
+		late_out[0] = f2_lo(fa);
+		late_out[1] = f2_hi(fa);
+		late_out[2] = f2_lo(fb);
+		late_out[3] = f2_hi(fb);
+		{
+			F2 ra = fa, rb = fb;
+			scatter2_reversed(ra, rb, c.mix_x, c.mix_y);
+			ring.st(lline0 + 0 * lline_len + (pos & lline_mask), f2_hi(rb));
+			ring.st(lline0 + 1 * lline_len + (pos & lline_mask), f2_lo(rb));
+			ring.st(lline0 + 2 * lline_len + (pos & lline_mask), f2_hi(ra));
+			ring.st(lline0 + 3 * lline_len + (pos & lline_mask), f2_lo(ra));
 		}
 
 		offset += 1;
@@ -489,6 +545,18 @@ struct FxReverbT {
 		}
 
 		// ---- pan the 8 line outputs to the bus with stepped gains (oalsfxpp.cpp:6142-6166, 2752-2798) ----
+		if (pan_static && CT == 2) {
+			// acc[k] += d_l * gain[l][k], both output channels at once, lines in the reference's order
+			F2 accp = f2(acc[0], acc[1]);
+			OALSFX_UNROLL
+			for (int l = 0; l < 8; ++l) {
+				const float d = (l < 4 ? early_out[l] : late_out[l - 4]);
+				accp = accp + (f2_bcast(d) * f2(cur_gain[l][0], cur_gain[l][1]));
+			}
+			acc[0] = f2_lo(accp);
+			acc[1] = f2_hi(accp);
+			return;
+		}
 		if (pan_static) {
 			OALSFX_UNROLL
 			for (int l = 0; l < 8; ++l) {
@@ -530,10 +598,14 @@ struct FxReverbT {
 				store_words(lp[l], st + (kWLp + l * 4) * kLanes);
 				store_words(hp[l], st + (kWHp + l * 4) * kLanes);
 			}
-			st[(kWT60 + l * 4 + 0) * kLanes] = float_as_word(t60[l][0][0]);
-			st[(kWT60 + l * 4 + 1) * kLanes] = float_as_word(t60[l][0][1]);
-			st[(kWT60 + l * 4 + 2) * kLanes] = float_as_word(t60[l][1][0]);
-			st[(kWT60 + l * 4 + 3) * kLanes] = float_as_word(t60[l][1][1]);
+		}
+		OALSFX_UNROLL
+		for (int h = 0; h < 2; ++h) {
+			OALSFX_UNROLL
+			for (int w = 0; w < 4; ++w) {
+				st[(kWT60 + (2 * h) * 4 + w) * kLanes] = float_as_word(f2_lo(t60p[h][w >> 1][w & 1]));
+				st[(kWT60 + (2 * h + 1) * 4 + w) * kLanes] = float_as_word(f2_hi(t60p[h][w >> 1][w & 1]));
+			}
 		}
 		OALSFX_UNROLL
 		for (int l = 0; l < 8; ++l) {
