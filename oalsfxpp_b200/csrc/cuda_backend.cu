@@ -191,15 +191,17 @@ public:
 		return check(cudaGetLastError(), kernel_name(kernel_id));
 	}
 
-	// The duo kernels stream through per-warp shared-memory windows (~29 KB per CTA) and have no use
-	// for L1: ask for the largest shared-memory carve-out so residency is register-limited (6 CTAs
-	// per SM) instead of stopping at the driver's default split (ncu: launch__occupancy_limit_shared_mem).
+	// The duo kernels stream through per-warp shared-memory windows (~30 KB per CTA) AND lean on L1:
+	// the stream-major I/O rows are read and written 4 bytes per lane per frame, so each 128-byte line is
+	// touched by 16 consecutive frames.  Measured on B200 (gpurun_out/exp13, 65 536 streams): carve-out
+	// 58-66 % (4 CTAs per SM, ~80-96 KB of L1) 3.14 ms; 72-84 % (5 CTAs) 3.38 ms; 100 % (6 CTAs, ~28 KB
+	// of L1) 3.80 ms; 50 % (3 CTAs) 3.22 ms.
 	template <class K> void prefer_shared(int id, K kernel)
 	{
 		if (!carveout_done_[id]) {
 			// tuning knobs (experiments only): OALSFX_TUNE_CARVEOUT = percent or -1 (driver default),
 			// OALSFX_TUNE_DYN_SMEM = bytes of unused dynamic shared memory per CTA (caps residency)
-			int carveout = cudaSharedmemCarveoutMaxShared;
+			int carveout = 62;
 			if (const char* e = getenv("OALSFX_TUNE_CARVEOUT")) {
 				carveout = atoi(e);
 			}

@@ -34,7 +34,7 @@ namespace duo {
 #endif
 
 constexpr int kDuoUnroll = OALSFX_DUO_UNROLL;
-constexpr int kDuoChunk = 16;          // frames per hand-off
+constexpr int kDuoChunk = 4;           // frames per hand-off
 constexpr int kBarFull = 0;            // named barriers 0,1: buffer b filled by the front warp
 constexpr int kBarEmpty = 2;           // named barriers 2,3: buffer b drained by the back warp
 
@@ -122,21 +122,32 @@ __global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(
 		r1.begin(a, 1, tile, lane, m1 ? col : e1 ? col + 2 * kLanes : nullptr);
 		r2.begin(a, 2, tile, lane, m2 ? col : e2 ? col + 2 * kLanes : nullptr);
 		// Everything long-latency of sample i + kFwDepth is requested while sample i is computed.
-		auto issue = [&](int ahead, int frame) {
-			r0.fx.prefetch_issue(a.slot[0], ahead);
-			r1.fx.prefetch_issue(a.slot[1], ahead);
-			r2.fx.prefetch_issue(a.slot[2], ahead);
+		const unsigned col_s = smem_addr(col);
+		const float* in = src;                // input frame being requested (advances with `frame`)
+		auto issue_input = [&](int frame) {
 			if (io_ok && frame < a.frames) {
+				const unsigned slot = col_s + static_cast<unsigned>(((frame & (kFwSlots - 1)) * kFwSlotFloats + 4 * kLanes) * 4);
 #pragma unroll
 				for (int c = 0; c < CT; ++c) {
-					cp_async_f32(col + (frame & (kFwSlots - 1)) * kFwSlotFloats + (4 + c) * kLanes, src + frame * a.io_fs + c * a.io_cs);
+					cp_async_f32_s(slot + c * kLanes * 4, in + c * a.io_cs);
 				}
 			}
+			in += a.io_fs;
+		};
+		for (int k = 0; k < kFwDepth; ++k) { // prime: samples 0 .. kFwDepth-1
+			r0.fx.prefetch_issue(a.slot[0], k);
+			r1.fx.prefetch_issue(a.slot[1], k);
+			r2.fx.prefetch_issue(a.slot[2], k);
+			issue_input(k);
+			cp_async_commit_group();
+		}
+		auto issue = [&](int frame) {        // steady state: sample `frame` = current + kFwDepth
+			r0.fx.prefetch_next(a.slot[0]);
+			r1.fx.prefetch_next(a.slot[1]);
+			r2.fx.prefetch_next(a.slot[2]);
+			issue_input(frame);
 			cp_async_commit_group();
 		};
-		for (int k = 0; k < kFwDepth; ++k) {
-			issue(k, k);
-		}
 		for (int ci = 0; ci < chunks; ++ci) {
 			const int b = ci & 1;
 			const int first = ci * kDuoChunk;
@@ -146,20 +157,17 @@ __global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(
 			for (int f = 0; f < count; ++f) {
 				const int i = first + f;
 				float x[CT], acc[CT];
-				issue(kFwDepth, i + kFwDepth);
+				issue(i + kFwDepth);
 				cp_async_wait_group<kFwDepth>();
 #pragma unroll
 				for (int c = 0; c < CT; ++c) {
 					x[c] = io_ok ? col[(i & (kFwSlots - 1)) * kFwSlotFloats + (4 + c) * kLanes] : 0.0F;
 					acc[c] = 0.0F;
 				}
-				// direct send (oalsfxpp.cpp:2924-2950)
+				// direct send (oalsfxpp.cpp:2924-2950); gains sanitized by the host
 #pragma unroll
 				for (int c = 0; c < CT; ++c) {
-#pragma unroll
-					for (int k = 0; k < CT; ++k) {
-						acc[k] += x[c] * a.direct.gains[c][k]; // gains sanitized by the host
-					}
+					pan_add<CT, true>(acc, CT, a.direct.gains[c], x[c]);
 				}
 				r0.step(a, 0, x, acc);
 				r1.step(a, 1, x, acc);

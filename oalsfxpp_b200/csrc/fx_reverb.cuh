@@ -123,8 +123,16 @@ struct FxReverbT {
 	bool primed, can_pf;
 	bool pan_static;   // this sub-chunk: no gain ramps and every one of the 8 x C pan gains is audible
 
-	OALSFX_HD void set_prefetch(float* column) { pf_col = column; }
+	unsigned pf_s;     // shared-space address of the warp's window (lane offset removed), device build
+	OALSFX_HD void set_prefetch(float* column)
+	{
+		pf_col = column;
+#if defined(__CUDA_ARCH__)
+		pf_s = column ? smem_addr(column) - (threadIdx.x % kLanes) * 4U : 0U;
+#endif
+	}
 	OALSFX_HD void prefetch_issue(const SlotCoef&, int) {} // the reverb runs its own pipeline inside step()
+	OALSFX_HD void prefetch_next(const SlotCoef&) {}
 
 	OALSFX_HD int32_t old_tap(int group, int line) const
 	{
@@ -370,17 +378,17 @@ struct FxReverbT {
 		const int lane = threadIdx.x % kLanes;
 		const int q4 = (lane & 7) * 4;
 		const int ps = p4 + (lane >> 3);
-		float* dst = pf_col - lane + (ps & (kPfSlots - 1)) * (kPfTaps * kLanes) + q4;
+		const unsigned dst = pf_s + static_cast<unsigned>(((ps & (kPfSlots - 1)) * (kPfTaps * kLanes) + q4) * 4);
 		const float* src = ring.p - lane + q4;
 		const int len0 = c.mask[0] + 1, len1 = c.mask[1] + 1, len2 = c.mask[2] + 1, len3 = c.mask[3] + 1, len4 = c.mask[4] + 1;
 #pragma unroll
 		for (int l = 0; l < 4; ++l) {
-			cp_async_16(dst + (0 + l) * kLanes, src + static_cast<unsigned>(c.ring_base[0] + l * len0 + ((ps - c.early_tap[l]) & c.mask[0])) * kLanes);
-			cp_async_16(dst + (4 + l) * kLanes, src + static_cast<unsigned>(c.ring_base[1] + l * len1 + ((ps - c.early_ap_off[l]) & c.mask[1])) * kLanes);
-			cp_async_16(dst + (8 + l) * kLanes, src + static_cast<unsigned>(c.ring_base[2] + l * len2 + ((ps - c.early_off[l]) & c.mask[2])) * kLanes);
-			cp_async_16(dst + (12 + l) * kLanes, src + static_cast<unsigned>(c.ring_base[0] + l * len0 + ((ps - c.late_tap[l]) & c.mask[0])) * kLanes);
-			cp_async_16(dst + (16 + l) * kLanes, src + static_cast<unsigned>(c.ring_base[4] + l * len4 + ((ps - c.late_off[l]) & c.mask[4])) * kLanes);
-			cp_async_16(dst + (20 + l) * kLanes, src + static_cast<unsigned>(c.ring_base[3] + l * len3 + ((ps - c.late_ap_off[l]) & c.mask[3])) * kLanes);
+			cp_async_16_s(dst + (0 + l) * kLanes * 4, src + static_cast<unsigned>(c.ring_base[0] + l * len0 + ((ps - c.early_tap[l]) & c.mask[0])) * kLanes);
+			cp_async_16_s(dst + (4 + l) * kLanes * 4, src + static_cast<unsigned>(c.ring_base[1] + l * len1 + ((ps - c.early_ap_off[l]) & c.mask[1])) * kLanes);
+			cp_async_16_s(dst + (8 + l) * kLanes * 4, src + static_cast<unsigned>(c.ring_base[2] + l * len2 + ((ps - c.early_off[l]) & c.mask[2])) * kLanes);
+			cp_async_16_s(dst + (12 + l) * kLanes * 4, src + static_cast<unsigned>(c.ring_base[0] + l * len0 + ((ps - c.late_tap[l]) & c.mask[0])) * kLanes);
+			cp_async_16_s(dst + (16 + l) * kLanes * 4, src + static_cast<unsigned>(c.ring_base[4] + l * len4 + ((ps - c.late_off[l]) & c.mask[4])) * kLanes);
+			cp_async_16_s(dst + (20 + l) * kLanes * 4, src + static_cast<unsigned>(c.ring_base[3] + l * len3 + ((ps - c.late_ap_off[l]) & c.mask[3])) * kLanes);
 		}
 		cp_async_commit_group();
 	}
@@ -640,6 +648,7 @@ struct FxReverbInput {
 
 	OALSFX_HD void set_prefetch(float*) {}
 	OALSFX_HD void prefetch_issue(const SlotCoef&, int) {}
+	OALSFX_HD void prefetch_next(const SlotCoef&) {}
 
 	template <int CT>
 	OALSFX_HD void begin(const SlotCoef&, uint32_t* st, float* ring_p, bool, int, int)

@@ -119,19 +119,31 @@ struct SlotRunner {
 		}
 		const SendCoef& sc = a.aux[p];
 		float wet[kWetChannels] = {0.0F, 0.0F, 0.0F, 0.0F};
-		OALSFX_UNROLL
-		for (int c = 0; c < (CT ? CT : kMaxChannels); ++c) {
-			if (CT || c < a.channels) {
-				const float v = SF ? send_filter_step(sc, hist[SF ? c : 0], x[c]) : x[c];
-				OALSFX_UNROLL
-				for (int k = 0; k < kWetChannels; ++k) {
-					if (!SF || audible(sc.gains[c][k])) {
-						wet[k] += v * sc.gains[c][k];
+		if (CT == 2 && !SF) {
+			// wet[k] = (0 + x0 * g[0][k]) + x1 * g[1][k], wet channels (0,1) and (2,3) as pairs
+			const F2 zero = f2(0.0F, 0.0F), x0 = f2_bcast(x[0]), x1 = f2_bcast(x[1]);
+			const F2 wa = (zero + (x0 * f2(sc.gains[0][0], sc.gains[0][1]))) + (x1 * f2(sc.gains[1][0], sc.gains[1][1]));
+			const F2 wb = (zero + (x0 * f2(sc.gains[0][2], sc.gains[0][3]))) + (x1 * f2(sc.gains[1][2], sc.gains[1][3]));
+			wet[0] = f2_lo(wa);
+			wet[1] = f2_hi(wa);
+			wet[2] = f2_lo(wb);
+			wet[3] = f2_hi(wb);
+			fx.template step<CT, true>(a.slot[p], wet, acc, a.channels);
+		} else {
+			OALSFX_UNROLL
+			for (int c = 0; c < (CT ? CT : kMaxChannels); ++c) {
+				if (CT || c < a.channels) {
+					const float v = SF ? send_filter_step(sc, hist[SF ? c : 0], x[c]) : x[c];
+					OALSFX_UNROLL
+					for (int k = 0; k < kWetChannels; ++k) {
+						if (!SF || audible(sc.gains[c][k])) {
+							wet[k] += v * sc.gains[c][k];
+						}
 					}
 				}
 			}
+			fx.template step<CT, !SF>(a.slot[p], wet, acc, a.channels);
 		}
-		fx.template step<CT, !SF>(a.slot[p], wet, acc, a.channels);
 	}
 
 	// Effect state only (the caller writes the send filter history itself).

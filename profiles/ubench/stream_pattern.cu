@@ -58,6 +58,77 @@ __global__ void __launch_bounds__(64) pattern(const float* __restrict__ rd, floa
 	if (acc == 12345.678f) *sink = acc;
 }
 
+// Mixed granularity: every "sample group" of 4 positions reads NR rings with GR-line accesses and writes NW rings
+// with GW-line accesses (GR, GW in {1, 4}): the shape of "batched reads, per-sample writes" vs "both batched".
+template <int GR, int GW>
+__global__ void __launch_bounds__(64) mixed(const float* __restrict__ rd, float* __restrict__ wr, long long ring_floats, int lines,
+	int groups, int start, float* sink)
+{
+	const int lane = threadIdx.x & 31;
+	const long long tile = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+	const float* r = rd + tile * NR * ring_floats;
+	float* w = wr + tile * NW * ring_floats;
+	float acc = 0.f;
+	for (int g = 0; g < groups; ++g) {
+		const int p4 = ((start + g) * 4);
+		if (GR == 4) {
+			float4 v[NR];
+#pragma unroll
+			for (int k = 0; k < NR; ++k) {
+				const int pos = (p4 + k * 3908) & (lines - 1);
+				v[k] = *reinterpret_cast<const float4*>(r + k * ring_floats + (long long)pos * 32 + lane * 4);
+			}
+#pragma unroll
+			for (int k = 0; k < NR; ++k) acc += v[k].x + v[k].y + v[k].z + v[k].w;
+		} else {
+#pragma unroll
+			for (int s = 0; s < 4; ++s) {
+				float v[NR];
+#pragma unroll
+				for (int k = 0; k < NR; ++k) {
+					const int pos = (p4 + s + k * 3908) & (lines - 1);
+					v[k] = r[k * ring_floats + (long long)pos * 32 + lane];
+				}
+#pragma unroll
+				for (int k = 0; k < NR; ++k) acc += v[k];
+			}
+		}
+		if (GW == 4) {
+#pragma unroll
+			for (int k = 0; k < NW; ++k) {
+				const int pos = (p4 + k * 5636) & (lines - 1);
+				*reinterpret_cast<float4*>(w + k * ring_floats + (long long)pos * 32 + lane * 4) = make_float4(acc, acc + k, acc, acc);
+			}
+		} else {
+#pragma unroll
+			for (int s = 0; s < 4; ++s)
+#pragma unroll
+				for (int k = 0; k < NW; ++k) {
+					const int pos = (p4 + s + k * 5636) & (lines - 1);
+					w[k * ring_floats + (long long)pos * 32 + lane] = acc + k + s;
+				}
+		}
+	}
+	if (acc == 12345.678f) *sink = acc;
+}
+
+template <int GR, int GW> void run_mixed(const float* rd, float* wr, long long ring_floats, int lines, int tiles, float* sink)
+{
+	const int samples = 2048, groups = samples / 4;
+	cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+	float best = 1e9f;
+	for (int rep = 0; rep < 4; ++rep) {
+		cudaEventRecord(e0);
+		mixed<GR, GW><<<tiles / 2, 64>>>(rd, wr, ring_floats, lines, groups, rep * groups, sink);
+		cudaEventRecord(e1); cudaEventSynchronize(e1);
+		float ms; cudaEventElapsedTime(&ms, e0, e1);
+		if (rep && ms < best) best = ms;
+	}
+	const double bytes = double(tiles) * samples * (NR + NW) * 128.0;
+	printf("  reads %d B/visit, writes %d B/visit: %.3f ms, %5.0f GB/s [%s]\n", GR * 128, GW * 128, best, bytes / best * 1e-6,
+		cudaGetErrorString(cudaGetLastError()));
+}
+
 template <int G, int U> void run(const float* rd, float* wr, long long ring_floats, int lines, int tiles, int mode, float* sink)
 {
 	const int samples = 2048, visits = samples / G;
@@ -87,6 +158,11 @@ int main(int argc, char** argv)
 	cudaMemset(rd, 0, sizeof(float) * ring_floats * NR * tiles);
 	cudaMemset(wr, 0, sizeof(float) * ring_floats * NW * tiles);
 	printf("tiles %d, footprint %.1f GB\n", tiles, sizeof(float) * ring_floats * (NR + NW) * tiles * 1e-9);
+	printf("mixed granularity (read+write)\n");
+	run_mixed<1, 1>(rd, wr, ring_floats, lines, tiles, sink);
+	run_mixed<4, 1>(rd, wr, ring_floats, lines, tiles, sink);
+	run_mixed<1, 4>(rd, wr, ring_floats, lines, tiles, sink);
+	run_mixed<4, 4>(rd, wr, ring_floats, lines, tiles, sink);
 	const char* names[3] = {"read+write", "read only", "write only"};
 	for (int mode = 0; mode < 3; ++mode) {
 		printf("%s\n", names[mode]);
