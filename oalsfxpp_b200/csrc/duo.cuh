@@ -105,6 +105,25 @@ __global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(
 	float* dst = a.dst + tile * a.io_ts + lane * a.io_ls;
 	uint32_t* ss = a.send_state + (static_cast<long long>(tile) * kSendStateWords) * kLanes + lane;
 	const int chunks = (a.frames + kDuoChunk - 1) / kDuoChunk;
+	// Row-batched I/O: with interleaved frames (the reference's buffer layout, one row per stream) a
+	// thread's kDuoChunk = 4 frames x 2 channels are 32 contiguous bytes of its row -- one full sector,
+	// moved with two 16-byte accesses per hand-off instead of eight scattered 4-byte ones (which lean on
+	// L1 to merge 16 frames per line and reach L2 as partial-sector writes).
+	static_assert(kDuoChunk == 4, "the row-batched I/O path moves 4 frames per hand-off");
+	__shared__ float xin[kDuoChunk][CT][kLanes];        // front warp: the current hand-off's input frames
+// Measured (gpurun_out/exp15): batching the OUTPUT rows helps (5 CTAs/SM: 3.38 -> 3.19 ms); batching the
+// INPUT rows hurts (3.17 -> 3.7 ms): 4-byte requests let L1 fetch each 128-byte row segment from DRAM once
+// and serve 16 frames from it, 16-byte requests fetch it as four separate sectors 4 frames apart.
+#ifndef OALSFX_DUO_FAST_IN
+#define OALSFX_DUO_FAST_IN 0
+#endif
+#ifndef OALSFX_DUO_FAST_OUT
+#define OALSFX_DUO_FAST_OUT 1
+#endif
+	const bool fast_rows = CT == 2 && a.io_cs == 1 && a.io_fs == CT && (a.frames % kDuoChunk) == 0 && (a.io_ls % 4) == 0 &&
+		(a.io_ts % 4) == 0 && ((reinterpret_cast<unsigned long long>(a.src) | reinterpret_cast<unsigned long long>(a.dst)) & 15ULL) == 0;
+	const bool fast_io = fast_rows && OALSFX_DUO_FAST_IN;   // input side
+	const bool fast_out = fast_rows && OALSFX_DUO_FAST_OUT; // output side
 
 	if (front) {
 		SlotRunner<CT, false, F0> r0;
@@ -125,7 +144,7 @@ __global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(
 		const unsigned col_s = smem_addr(col);
 		const float* in = src;                // input frame being requested (advances with `frame`)
 		auto issue_input = [&](int frame) {
-			if (io_ok && frame < a.frames) {
+			if (!fast_io && io_ok && frame < a.frames) {
 				const unsigned slot = col_s + static_cast<unsigned>(((frame & (kFwSlots - 1)) * kFwSlotFloats + 4 * kLanes) * 4);
 #pragma unroll
 				for (int c = 0; c < CT; ++c) {
@@ -134,6 +153,12 @@ __global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(
 			}
 			in += a.io_fs;
 		};
+		float4 nx0 = make_float4(0.0F, 0.0F, 0.0F, 0.0F), nx1 = nx0; // the next hand-off's input frames (fast_io)
+		if (fast_io && io_ok) {
+			const float4* row = reinterpret_cast<const float4*>(src);
+			nx0 = __ldcs(row);
+			nx1 = __ldcs(row + 1);
+		}
 		for (int k = 0; k < kFwDepth; ++k) { // prime: samples 0 .. kFwDepth-1
 			r0.fx.prefetch_issue(a.slot[0], k);
 			r1.fx.prefetch_issue(a.slot[1], k);
@@ -152,6 +177,23 @@ __global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(
 			const int b = ci & 1;
 			const int first = ci * kDuoChunk;
 			const int count = min(kDuoChunk, a.frames - first);
+			if (fast_io) {
+				// this hand-off's frames were requested one hand-off ago; request the next one's
+				const float4 c0 = nx0, c1 = nx1;
+				if (io_ok && ci + 1 < chunks) {
+					const float4* row = reinterpret_cast<const float4*>(src + (first + kDuoChunk) * CT);
+					nx0 = __ldcs(row);
+					nx1 = __ldcs(row + 1);
+				}
+				xin[0][0][lane] = c0.x;
+				xin[0][1 % CT][lane] = c0.y;
+				xin[1][0][lane] = c0.z;
+				xin[1][1 % CT][lane] = c0.w;
+				xin[2][0][lane] = c1.x;
+				xin[2][1 % CT][lane] = c1.y;
+				xin[3][0][lane] = c1.z;
+				xin[3][1 % CT][lane] = c1.w;
+			}
 			bar_sync<kBarEmpty>(b);
 #pragma unroll (kDuoUnroll)
 			for (int f = 0; f < count; ++f) {
@@ -161,7 +203,7 @@ __global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(
 				cp_async_wait_group<kFwDepth>();
 #pragma unroll
 				for (int c = 0; c < CT; ++c) {
-					x[c] = io_ok ? col[(i & (kFwSlots - 1)) * kFwSlotFloats + (4 + c) * kLanes] : 0.0F;
+					x[c] = fast_io ? xin[f][c][lane] : io_ok ? col[(i & (kFwSlots - 1)) * kFwSlotFloats + (4 + c) * kLanes] : 0.0F;
 					acc[c] = 0.0F;
 				}
 				// direct send (oalsfxpp.cpp:2924-2950); gains sanitized by the host
@@ -223,12 +265,24 @@ __global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(
 				} else {
 					r3.step(a, 3, x, acc);
 				}
-				if (io_ok) {
+				if (fast_out) {
+#pragma unroll
+					for (int c = 0; c < CT; ++c) {
+						xch[b][f][kBusAt + c][lane] = acc[c]; // the finished frame replaces the partial bus (own column)
+					}
+				} else if (io_ok) {
 #pragma unroll
 					for (int c = 0; c < CT; ++c) {
 						dst[i * a.io_fs + c * a.io_cs] = acc[c];
 					}
 				}
+			}
+			if (fast_out && io_ok) {
+				float4* row = reinterpret_cast<float4*>(dst + first * CT);
+				__stcs(row, make_float4(xch[b][0][kBusAt][lane], xch[b][0][kBusAt + 1 % CT][lane], xch[b][1][kBusAt][lane],
+					xch[b][1][kBusAt + 1 % CT][lane]));
+				__stcs(row + 1, make_float4(xch[b][2][kBusAt][lane], xch[b][2][kBusAt + 1 % CT][lane], xch[b][3][kBusAt][lane],
+					xch[b][3][kBusAt + 1 % CT][lane]));
 			}
 			if (ci + 2 < chunks) {
 				bar_arrive<kBarEmpty>(b); // nobody waits for the last two drains
