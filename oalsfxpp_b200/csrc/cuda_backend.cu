@@ -14,6 +14,7 @@
 #include "kernel_table.h"
 #include "quad.cuh"
 #include "duo.cuh"
+#include "quartet.cuh"
 
 namespace oalsfx {
 namespace {
@@ -180,10 +181,16 @@ public:
 #undef OALSFX_QX
 #define OALSFX_DX(id, CT, F0, F1, F2, F3, twin) \
 		case id: \
-			prefer_shared(id, duo::duo_kernel<CT, F0, F1, F2, F3>); \
+			prefer_shared(id, duo::duo_kernel<CT, F0, F1, F2, F3>, 62); \
 			duo::duo_kernel<CT, F0, F1, F2, F3><<<static_cast<unsigned>(args.tile_count), 64, tune_dyn_smem_, st>>>(args); break;
 			OALSFX_DUO_TABLE(OALSFX_DX)
 #undef OALSFX_DX
+#define OALSFX_TX(id, CT, F0, F1, F2, F3, twin) \
+		case id: \
+			prefer_shared(id, quartet::quartet_kernel<CT, F0, F1, F2, F3>, 70); \
+			quartet::quartet_kernel<CT, F0, F1, F2, F3><<<static_cast<unsigned>(args.tile_count), quartet::kThreads, tune_dyn_smem_, st>>>(args); break;
+			OALSFX_QUARTET_TABLE(OALSFX_TX)
+#undef OALSFX_TX
 		default:
 			error_ = "unknown kernel id";
 			return false;
@@ -196,12 +203,12 @@ public:
 	// touched by 16 consecutive frames.  Measured on B200 (gpurun_out/exp13, 65 536 streams): carve-out
 	// 58-66 % (4 CTAs per SM, ~80-96 KB of L1) 3.14 ms; 72-84 % (5 CTAs) 3.38 ms; 100 % (6 CTAs, ~28 KB
 	// of L1) 3.80 ms; 50 % (3 CTAs) 3.22 ms.
-	template <class K> void prefer_shared(int id, K kernel)
+	template <class K> void prefer_shared(int id, K kernel, int default_carveout)
 	{
 		if (!carveout_done_[id]) {
 			// tuning knobs (experiments only): OALSFX_TUNE_CARVEOUT = percent or -1 (driver default),
 			// OALSFX_TUNE_DYN_SMEM = bytes of unused dynamic shared memory per CTA (caps residency)
-			int carveout = 62;
+			int carveout = default_carveout;
 			if (const char* e = getenv("OALSFX_TUNE_CARVEOUT")) {
 				carveout = atoi(e);
 			}

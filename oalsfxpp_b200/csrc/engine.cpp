@@ -100,8 +100,10 @@ struct oalsfx_engine {
 	std::vector<Group> groups;
 	bool groups_dirty = true;
 	long long launches = 0;
-	// Which fused kernel family serves whole-tile groups: 2 = duo (default), 1 = quad, 0 = the plain
-	// thread-per-stream twin.  OALSFX_KERNEL=duo|quad|single overrides (A/B measurements only).
+	// Which fused kernel family serves whole-tile groups: 2 = duo (default, the fastest measured),
+	// 3 = quartet (four-stage pipeline; falls back to duo for signatures without a quartet entry),
+	// 1 = quad, 0 = the plain thread-per-stream twin.  OALSFX_KERNEL=duo|quartet|quad|single overrides
+	// (A/B measurements and the parity tests of every family).
 	int family = 2;
 	// Host-buffer mix: tile slice the next launches are restricted to (0 = all tiles), and the
 	// engine-owned streams that overlap H2D, kernels and D2H of consecutive slices.
@@ -511,7 +513,9 @@ struct oalsfx_engine {
 			sanitize_gains(a);
 			const bool whole_tiles = g.identity || g.full_tiles;
 			int id = ki.id;
-			if (whole_tiles && family == 2 && duo_for_twin(ki.id) >= 0) {
+			if (whole_tiles && family == 3 && quartet_for_twin(ki.id) >= 0) {
+				id = quartet_for_twin(ki.id);
+			} else if (whole_tiles && family >= 2 && duo_for_twin(ki.id) >= 0) {
 				id = duo_for_twin(ki.id);
 			} else if (whole_tiles && family >= 1 && quad_for_twin(ki.id) >= 0) {
 				id = quad_for_twin(ki.id);
@@ -588,7 +592,7 @@ int oalsfx_engine_create(const oalsfx_engine_desc* desc, oalsfx_engine** out)
 	e->channels = dev.channels;
 	e->slots = desc->effect_count;
 	if (const char* fam = std::getenv("OALSFX_KERNEL")) {
-		e->family = (std::strcmp(fam, "single") == 0 ? 0 : std::strcmp(fam, "quad") == 0 ? 1 : 2);
+		e->family = (std::strcmp(fam, "single") == 0 ? 0 : std::strcmp(fam, "quad") == 0 ? 1 : std::strcmp(fam, "quartet") == 0 ? 3 : 2);
 	}
 	e->be = make_backend(desc->device, g_create_error);
 	if (!e->be) {

@@ -32,7 +32,7 @@ namespace oalsfx {
 constexpr int kPfBatch = 4;                 // ring positions per batched copy (32 lanes x 16 B = 4 lines)
 constexpr int kPfSlots = 2 * kPfBatch;      // power of two
 constexpr int kPfDepth = kPfSlots - 1;      // furthest position requested beyond the current one
-constexpr int kPfTaps = 24;
+constexpr int kPfTaps = 24;                 // whole effect; a half (FxReverbT<.., EARLY, LATE>) uses 12
 constexpr int kPfWarpFloats = kPfSlots * kPfTaps * kLanes; // 24 KiB per reverb warp
 
 // Input stage of the reverb, shared by the whole effect (FxReverbT<true>) and by FxReverbInput,
@@ -84,8 +84,19 @@ OALSFX_HD void reverb_input_stage(const ReverbCoef& c, const float* wet, BiquadH
 
 // INPUT = false: the input stage (and the lp/hp filter history words of the state) belong to a
 // FxReverbInput running in another warp; `wet` is not read.
-template <bool INPUT>
+// EARLY / LATE: which half of the sample body this instance runs.  The halves only meet in the main
+// delay line (early -> late feed) and in the order of the pan adds (early lines first), so they can
+// run in two warps, the late one behind the early one (quartet.cuh).  Each half keeps its own copy of
+// the block-partition / cross-fade bookkeeping (it evolves identically in both), owns its lines' pan
+// gains, its three OLD tap groups and -- the late half -- the T60 / modulator state and the scalars.
+template <bool INPUT, bool EARLY = true, bool LATE = true>
 struct FxReverbT {
+	static_assert(EARLY || LATE, "a reverb instance runs at least one half");
+	static_assert(!INPUT || (EARLY && LATE), "the input stage is only bundled with the whole effect");
+	static constexpr int kLine0 = EARLY ? 0 : 4, kLine1 = LATE ? 8 : 4;     // pan lines [kLine0, kLine1)
+	static constexpr int kTap0 = EARLY ? 0 : 12;                            // first window tap of this instance
+	static constexpr int kTaps = (EARLY ? 12 : 0) + (LATE ? 12 : 0);        // window taps per ring position
+	static constexpr int kWindowFloats = kPfSlots * kTaps * kLanes;
 	// Layout of the slot state in HBM (words, per lane).  Only the hot part lives in registers.
 	struct State {
 		BiquadHist lp[4], hp[4];
@@ -156,12 +167,14 @@ struct FxReverbT {
 		for (int h = 0; h < 2; ++h) {
 			OALSFX_UNROLL
 			for (int w = 0; w < 4; ++w) {
-				t60p[h][w >> 1][w & 1] = f2(word_as_float(st[(kWT60 + (2 * h) * 4 + w) * kLanes]),
-					word_as_float(st[(kWT60 + (2 * h + 1) * 4 + w) * kLanes]));
+				if (LATE) {
+					t60p[h][w >> 1][w & 1] = f2(word_as_float(st[(kWT60 + (2 * h) * 4 + w) * kLanes]),
+						word_as_float(st[(kWT60 + (2 * h + 1) * 4 + w) * kLanes]));
+				}
 			}
 		}
 		OALSFX_UNROLL
-		for (int l = 0; l < 8; ++l) {
+		for (int l = kLine0; l < kLine1; ++l) {
 			OALSFX_UNROLL
 			for (int k = 0; k < (CT ? CT : kMaxChannels); ++k) {
 				if (CT || k < channels) {
@@ -179,8 +192,10 @@ struct FxReverbT {
 		}
 		if (update) {
 			// update_modulator (oalsfxpp.cpp:7028-7030)
-			mod_index = static_cast<int32_t>(mod_index * static_cast<int64_t>(c.mod_range) / mod_range);
-			mod_range = c.mod_range;
+			if (LATE) {
+				mod_index = static_cast<int32_t>(mod_index * static_cast<int64_t>(c.mod_range) / mod_range);
+				mod_range = c.mod_range;
+			}
 			// "Determine if delay-line cross-fading is required" (oalsfxpp.cpp:6061-6075)
 			bool differs = false;
 			for (int i = 0; i < 4; ++i) {
@@ -228,11 +243,15 @@ struct FxReverbT {
 		// Reading kPfDepth samples ahead is legal when nothing written during those samples can be what
 		// the prefetch reads: every delay > kPfDepth, the late taps that far beyond the late feed write,
 		// no cross-fade (reads both tap sets), no modulation (the late line read position moves).
-		bool ok = pf_col != nullptr && !faded && c.mod_depth == 0.0F && mod_filter == 0.0F;
+		bool ok = pf_col != nullptr && !faded && (!LATE || (c.mod_depth == 0.0F && mod_filter == 0.0F));
 		OALSFX_UNROLL
 		for (int l = 0; l < 4; ++l) {
-			ok = ok && c.early_tap[l] > kPfDepth && c.early_ap_off[l] > kPfDepth && c.early_off[l] > kPfDepth &&
-				c.late_tap[l] > c.late_feed_tap + kPfDepth && c.late_ap_off[l] > kPfDepth && c.late_off[l] > kPfDepth;
+			if (EARLY) {
+				ok = ok && c.early_tap[l] > kPfDepth && c.early_ap_off[l] > kPfDepth && c.early_off[l] > kPfDepth;
+			}
+			if (LATE) {
+				ok = ok && c.late_tap[l] > c.late_feed_tap + kPfDepth && c.late_ap_off[l] > kPfDepth && c.late_off[l] > kPfDepth;
+			}
 		}
 		can_pf = ok;
 		pan_static = true;
@@ -241,7 +260,7 @@ struct FxReverbT {
 		ramp_mask[0] = ramp_mask[1] = 0;
 		active_mask[0] = active_mask[1] = 0;
 		OALSFX_UNROLL
-		for (int l = 0; l < 8; ++l) {
+		for (int l = kLine0; l < kLine1; ++l) {
 			const float* target = (l < 4 ? c.pan_early[l] : c.pan_late[l - 4]);
 			OALSFX_UNROLL
 			for (int k = 0; k < (CT ? CT : kMaxChannels); ++k) {
@@ -280,20 +299,24 @@ struct FxReverbT {
 			if (fade_count >= kFadeSamples) {
 				fade_count = kFadeSamples;
 				fade = 1.0F;
-				for (int i = 0; i < 4; ++i) { // commit the new tap sets
-					st_mem[(kWOld + 0 + i) * kLanes] = static_cast<uint32_t>(c.early_tap[i]);
-					st_mem[(kWOld + 4 + i) * kLanes] = static_cast<uint32_t>(c.early_ap_off[i]);
-					st_mem[(kWOld + 8 + i) * kLanes] = static_cast<uint32_t>(c.early_off[i]);
-					st_mem[(kWOld + 12 + i) * kLanes] = static_cast<uint32_t>(c.late_tap[i]);
-					st_mem[(kWOld + 16 + i) * kLanes] = static_cast<uint32_t>(c.late_ap_off[i]);
-					st_mem[(kWOld + 20 + i) * kLanes] = static_cast<uint32_t>(c.late_off[i]);
+				for (int i = 0; i < 4; ++i) { // commit the new tap sets (each half its own groups)
+					if (EARLY) {
+						st_mem[(kWOld + 0 + i) * kLanes] = static_cast<uint32_t>(c.early_tap[i]);
+						st_mem[(kWOld + 4 + i) * kLanes] = static_cast<uint32_t>(c.early_ap_off[i]);
+						st_mem[(kWOld + 8 + i) * kLanes] = static_cast<uint32_t>(c.early_off[i]);
+					}
+					if (LATE) {
+						st_mem[(kWOld + 12 + i) * kLanes] = static_cast<uint32_t>(c.late_tap[i]);
+						st_mem[(kWOld + 16 + i) * kLanes] = static_cast<uint32_t>(c.late_ap_off[i]);
+						st_mem[(kWOld + 20 + i) * kLanes] = static_cast<uint32_t>(c.late_off[i]);
+					}
 				}
 			}
 		}
 		const bool ramp_done = (sub_todo == block_frames - base); // `pos == counter`
 		if (ramp_done) {
 			OALSFX_UNROLL
-			for (int l = 0; l < 8; ++l) {
+			for (int l = kLine0; l < kLine1; ++l) {
 				const float* target = (l < 4 ? c.pan_early[l] : c.pan_late[l - 4]);
 				OALSFX_UNROLL
 				for (int k = 0; k < (CT ? CT : kMaxChannels); ++k) {
@@ -311,7 +334,7 @@ struct FxReverbT {
 	OALSFX_HD float tap(int tap_index, int ring_word0, int mask, int pos, int group, int line, int new_d, float mu) const
 	{
 		if (PF) {
-			return pf_cur[tap_index * kLanes];
+			return pf_cur[(tap_index - kTap0) * kLanes];
 		}
 		if (!faded) {
 			return ring.ld(ring_word0 + ((pos - new_d) & mask)); // committed: old == new
@@ -378,17 +401,21 @@ struct FxReverbT {
 		const int lane = threadIdx.x % kLanes;
 		const int q4 = (lane & 7) * 4;
 		const int ps = p4 + (lane >> 3);
-		const unsigned dst = pf_s + static_cast<unsigned>(((ps & (kPfSlots - 1)) * (kPfTaps * kLanes) + q4) * 4);
+		const unsigned dst = pf_s + static_cast<unsigned>(((ps & (kPfSlots - 1)) * (kTaps * kLanes) + q4) * 4);
 		const float* src = ring.p - lane + q4;
 		const int len0 = c.mask[0] + 1, len1 = c.mask[1] + 1, len2 = c.mask[2] + 1, len3 = c.mask[3] + 1, len4 = c.mask[4] + 1;
 #pragma unroll
 		for (int l = 0; l < 4; ++l) {
-			cp_async_16_s(dst + (0 + l) * kLanes * 4, src + static_cast<unsigned>(c.ring_base[0] + l * len0 + ((ps - c.early_tap[l]) & c.mask[0])) * kLanes);
-			cp_async_16_s(dst + (4 + l) * kLanes * 4, src + static_cast<unsigned>(c.ring_base[1] + l * len1 + ((ps - c.early_ap_off[l]) & c.mask[1])) * kLanes);
-			cp_async_16_s(dst + (8 + l) * kLanes * 4, src + static_cast<unsigned>(c.ring_base[2] + l * len2 + ((ps - c.early_off[l]) & c.mask[2])) * kLanes);
-			cp_async_16_s(dst + (12 + l) * kLanes * 4, src + static_cast<unsigned>(c.ring_base[0] + l * len0 + ((ps - c.late_tap[l]) & c.mask[0])) * kLanes);
-			cp_async_16_s(dst + (16 + l) * kLanes * 4, src + static_cast<unsigned>(c.ring_base[4] + l * len4 + ((ps - c.late_off[l]) & c.mask[4])) * kLanes);
-			cp_async_16_s(dst + (20 + l) * kLanes * 4, src + static_cast<unsigned>(c.ring_base[3] + l * len3 + ((ps - c.late_ap_off[l]) & c.mask[3])) * kLanes);
+			if (EARLY) {
+				cp_async_16_s(dst + (0 - kTap0 + l) * kLanes * 4, src + static_cast<unsigned>(c.ring_base[0] + l * len0 + ((ps - c.early_tap[l]) & c.mask[0])) * kLanes);
+				cp_async_16_s(dst + (4 - kTap0 + l) * kLanes * 4, src + static_cast<unsigned>(c.ring_base[1] + l * len1 + ((ps - c.early_ap_off[l]) & c.mask[1])) * kLanes);
+				cp_async_16_s(dst + (8 - kTap0 + l) * kLanes * 4, src + static_cast<unsigned>(c.ring_base[2] + l * len2 + ((ps - c.early_off[l]) & c.mask[2])) * kLanes);
+			}
+			if (LATE) {
+				cp_async_16_s(dst + (12 - kTap0 + l) * kLanes * 4, src + static_cast<unsigned>(c.ring_base[0] + l * len0 + ((ps - c.late_tap[l]) & c.mask[0])) * kLanes);
+				cp_async_16_s(dst + (16 - kTap0 + l) * kLanes * 4, src + static_cast<unsigned>(c.ring_base[4] + l * len4 + ((ps - c.late_off[l]) & c.mask[4])) * kLanes);
+				cp_async_16_s(dst + (20 - kTap0 + l) * kLanes * 4, src + static_cast<unsigned>(c.ring_base[3] + l * len3 + ((ps - c.late_ap_off[l]) & c.mask[3])) * kLanes);
+			}
 		}
 		cp_async_commit_group();
 	}
@@ -398,14 +425,14 @@ struct FxReverbT {
 	OALSFX_HD void step(const SlotCoef& sc, const float* wet, float* acc, int channels)
 	{
 		const ReverbCoef& c = sc.u.reverb;
-		if (sub_left == 0) {
+		if (OALSFX_UNLIKELY(sub_left == 0)) {
 			begin_sub<CT>(c, channels);
 		}
 		const int pos = offset;
 #if defined(__CUDA_ARCH__)
 		// The batched copies are a whole-warp affair (a lane fetches other lanes' streams), so the
 		// decision is a vote: every lane of the tile must be in the prefetchable state.
-		if (pf_col != nullptr && __all_sync(0xFFFFFFFFU, can_pf)) {
+		if (OALSFX_LIKELY(pf_col != nullptr && __all_sync(0xFFFFFFFFU, can_pf))) {
 			// Invariant while primed: the batch holding `pos` and the one after it have been requested.
 			const bool batch_start = (pos & (kPfBatch - 1)) == 0;
 			if (!primed || batch_start) {
@@ -420,7 +447,7 @@ struct FxReverbT {
 				cp_async_wait_group<1>(); // all but the newest batch: the one holding `pos` has landed
 				__syncwarp();             // ... for every lane's share of it
 			}
-			pf_cur = pf_col + (pos & (kPfSlots - 1)) * (kPfTaps * kLanes);
+			pf_cur = pf_col + (pos & (kPfSlots - 1)) * (kTaps * kLanes);
 			body<CT, true>(c, wet, acc, channels, pos); // branch-free: every read is a shared-memory load
 		} else {
 			primed = false;
@@ -430,7 +457,7 @@ struct FxReverbT {
 		body<CT, false>(c, wet, acc, channels, pos);
 #endif
 		sub_left -= 1;
-		if (sub_left == 0) {
+		if (OALSFX_UNLIKELY(sub_left == 0)) {
 			end_sub<CT>(c, channels);
 		}
 	}
@@ -451,8 +478,9 @@ struct FxReverbT {
 
 		// The four lines are carried as two pairs: a = lines (0, 1), b = lines (2, 3).
 		F2 fa, fb;
-		float early_out[4], late_out[4];
+		float early_out[4] = {0.0F, 0.0F, 0.0F, 0.0F}, late_out[4] = {0.0F, 0.0F, 0.0F, 0.0F};
 
+		if (EARLY) {
 		// ---- early reflections (oalsfxpp.cpp:7625-7672) ----
 		fa = f2(tap<PF>(0, main0 + 0 * main_len, main_mask, pos, 0, 0, c.early_tap[0], mu),
 			tap<PF>(1, main0 + 1 * main_len, main_mask, pos, 0, 1, c.early_tap[1], mu)) * f2(c.early_tap_coeff[0], c.early_tap_coeff[1]);
@@ -482,7 +510,9 @@ struct FxReverbT {
 			ring.st(main0 + 2 * main_len + feed, f2_hi(ra));
 			ring.st(main0 + 3 * main_len + feed, f2_lo(ra));
 		}
+		} // EARLY
 
+		if (LATE) {
 		// ---- late reverb (oalsfxpp.cpp:7735-7794) ----
 		// calc_modulation_delays (oalsfxpp.cpp:7443-7470); when depth and filter are both zero the
 		// product range*sinus is +-0 and the delay is 0 whatever the sinus is.
@@ -546,6 +576,7 @@ struct FxReverbT {
 			ring.st(lline0 + 2 * lline_len + (pos & lline_mask), f2_hi(ra));
 			ring.st(lline0 + 3 * lline_len + (pos & lline_mask), f2_lo(ra));
 		}
+		} // LATE
 
 		offset += 1;
 		if (faded) {
@@ -553,11 +584,11 @@ struct FxReverbT {
 		}
 
 		// ---- pan the 8 line outputs to the bus with stepped gains (oalsfxpp.cpp:6142-6166, 2752-2798) ----
-		if (pan_static && CT == 2) {
+		if (OALSFX_LIKELY(pan_static) && CT == 2) {
 			// acc[k] += d_l * gain[l][k], both output channels at once, lines in the reference's order
 			F2 accp = f2(acc[0], acc[1]);
 			OALSFX_UNROLL
-			for (int l = 0; l < 8; ++l) {
+			for (int l = kLine0; l < kLine1; ++l) {
 				const float d = (l < 4 ? early_out[l] : late_out[l - 4]);
 				accp = accp + (f2_bcast(d) * f2(cur_gain[l][0], cur_gain[l][1]));
 			}
@@ -567,7 +598,7 @@ struct FxReverbT {
 		}
 		if (pan_static) {
 			OALSFX_UNROLL
-			for (int l = 0; l < 8; ++l) {
+			for (int l = kLine0; l < kLine1; ++l) {
 				const float d = (l < 4 ? early_out[l] : late_out[l - 4]);
 				OALSFX_UNROLL
 				for (int k = 0; k < (CT ? CT : kMaxChannels); ++k) {
@@ -579,7 +610,7 @@ struct FxReverbT {
 			return;
 		}
 		OALSFX_UNROLL
-		for (int l = 0; l < 8; ++l) {
+		for (int l = kLine0; l < kLine1; ++l) {
 			const float d = (l < 4 ? early_out[l] : late_out[l - 4]);
 			OALSFX_UNROLL
 			for (int k = 0; k < (CT ? CT : kMaxChannels); ++k) {
@@ -611,12 +642,14 @@ struct FxReverbT {
 		for (int h = 0; h < 2; ++h) {
 			OALSFX_UNROLL
 			for (int w = 0; w < 4; ++w) {
-				st[(kWT60 + (2 * h) * 4 + w) * kLanes] = float_as_word(f2_lo(t60p[h][w >> 1][w & 1]));
-				st[(kWT60 + (2 * h + 1) * 4 + w) * kLanes] = float_as_word(f2_hi(t60p[h][w >> 1][w & 1]));
+				if (LATE) {
+					st[(kWT60 + (2 * h) * 4 + w) * kLanes] = float_as_word(f2_lo(t60p[h][w >> 1][w & 1]));
+					st[(kWT60 + (2 * h + 1) * 4 + w) * kLanes] = float_as_word(f2_hi(t60p[h][w >> 1][w & 1]));
+				}
 			}
 		}
 		OALSFX_UNROLL
-		for (int l = 0; l < 8; ++l) {
+		for (int l = kLine0; l < kLine1; ++l) {
 			OALSFX_UNROLL
 			for (int k = 0; k < (CT ? CT : kMaxChannels); ++k) {
 				if (CT || k < channels) {
@@ -624,11 +657,13 @@ struct FxReverbT {
 				}
 			}
 		}
-		st[(kWScalars + 0) * kLanes] = static_cast<uint32_t>(offset);
-		st[(kWScalars + 1) * kLanes] = static_cast<uint32_t>(fade_count);
-		st[(kWScalars + 2) * kLanes] = static_cast<uint32_t>(mod_index);
-		st[(kWScalars + 3) * kLanes] = static_cast<uint32_t>(mod_range);
-		st[(kWScalars + 4) * kLanes] = float_as_word(mod_filter);
+		if (LATE) { // the late half finishes last and owns the scalars
+			st[(kWScalars + 0) * kLanes] = static_cast<uint32_t>(offset);
+			st[(kWScalars + 1) * kLanes] = static_cast<uint32_t>(fade_count);
+			st[(kWScalars + 2) * kLanes] = static_cast<uint32_t>(mod_index);
+			st[(kWScalars + 3) * kLanes] = static_cast<uint32_t>(mod_range);
+			st[(kWScalars + 4) * kLanes] = float_as_word(mod_filter);
+		}
 #if defined(__CUDA_ARCH__)
 		cp_async_wait_group<0>(); // nothing of this warp's window may still be in flight when the CTA exits
 #endif
@@ -637,6 +672,8 @@ struct FxReverbT {
 
 using FxReverb = FxReverbT<true>;
 using FxReverbTail = FxReverbT<false>;
+using FxReverbEarly = FxReverbT<false, true, false>;
+using FxReverbLate = FxReverbT<false, false, true>;
 
 // The reverb's input stage alone, for a warp that runs ahead of the FxReverbTail of the same slot.
 // Shares the slot's state region: owns the lp/hp history words, reads (never writes) the offset.

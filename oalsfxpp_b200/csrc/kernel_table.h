@@ -47,6 +47,11 @@
 #define OALSFX_DUO_TABLE(DX) \
 	DX(kDuoChainStereo, 2, FxEqualizer, FxModDelay, FxEcho, FxReverb, kChainStereo)
 
+// Quartet kernels (quartet.cuh: four pipeline stages per tile -- dry + slot 0 | slots 1, 2 + reverb input |
+// reverb early half | reverb late half + output).  TX(id, CT, F0, F1, F2, F3, twin), same twin rule.
+#define OALSFX_QUARTET_TABLE(TX) \
+	TX(kQuartetChainStereo, 2, FxEqualizer, FxModDelay, FxEcho, FxReverb, kChainStereo)
+
 namespace oalsfx {
 
 enum KernelId : int {
@@ -61,8 +66,20 @@ enum KernelId : int {
 #define OALSFX_DX(id, CT, F0, F1, F2, F3, twin) id,
 	OALSFX_DUO_TABLE(OALSFX_DX)
 #undef OALSFX_DX
+#define OALSFX_TX(id, CT, F0, F1, F2, F3, twin) id,
+	OALSFX_QUARTET_TABLE(OALSFX_TX)
+#undef OALSFX_TX
 	kKernelEnd
 };
+
+// quartet kernel id for a thread-per-stream twin id, or -1
+inline int quartet_for_twin(int twin_id)
+{
+#define OALSFX_TX(id, CT, F0, F1, F2, F3, twin) if (twin_id == twin) return id;
+	OALSFX_QUARTET_TABLE(OALSFX_TX)
+#undef OALSFX_TX
+	return -1;
+}
 
 // duo kernel id for a thread-per-stream twin id, or -1
 inline int duo_for_twin(int twin_id)
@@ -90,6 +107,9 @@ inline int twin_of_quad(int quad_id)
 #define OALSFX_DX(id, CT, F0, F1, F2, F3, twin) if (quad_id == id) return twin;
 	OALSFX_DUO_TABLE(OALSFX_DX)
 #undef OALSFX_DX
+#define OALSFX_TX(id, CT, F0, F1, F2, F3, twin) if (quad_id == id) return twin;
+	OALSFX_QUARTET_TABLE(OALSFX_TX)
+#undef OALSFX_TX
 	return -1;
 }
 
@@ -149,6 +169,9 @@ inline const char* kernel_name(int id)
 #define OALSFX_DX(did, CT, F0, F1, F2, F3, twin) if (id == did) return #did;
 	OALSFX_DUO_TABLE(OALSFX_DX)
 #undef OALSFX_DX
+#define OALSFX_TX(tid, CT, F0, F1, F2, F3, twin) if (id == tid) return #tid;
+	OALSFX_QUARTET_TABLE(OALSFX_TX)
+#undef OALSFX_TX
 	return "?";
 }
 

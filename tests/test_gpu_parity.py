@@ -153,6 +153,40 @@ def test_cfg2_schedule_on_4096_streams(checker):
         _assert_match(expect, y[s], True, f"stream {s}")
 
 
+@pytest.mark.parametrize("family", ["quartet", "duo", "quad", "single"])
+def test_every_kernel_family_on_the_chain(checker, family, monkeypatch):
+    """The fused 4-slot stereo chain has four implementations (OALSFX_KERNEL, read when an engine is
+    created): the two-stage duo kernel (default), the four-stage quartet pipeline, the 4-lanes-per-stream
+    quad kernel and the plain thread-per-stream kernel.  Each must equal the checker bit for bit on a
+    schedule that exercises ramps (reverb gain), a tap cross-fade (reflections delay change in block 2),
+    an equalizer step, a block size that is not a multiple of 4 and a partially filled last tile."""
+    monkeypatch.setenv("OALSFX_KERNEL", family)
+    lib = _lib()
+    S = 160 + 7
+    blocks = [1024, 1024, 640, 333, 1024]
+    chain = [T.equalizer, T.chorus, T.echo, T.eax_reverb]
+    total = sum(blocks)
+    x = np.stack([H.noise(s, 2, total) for s in range(S)])
+    y = np.empty_like(x)
+    script = [("type", i, t) for i, t in enumerate(chain)] + [("apply",)]
+    with ox.Engine(S, F.stereo, 48000, 4, lib=lib) as eng:
+        for i, t in enumerate(chain):
+            eng.set_effect(i, t)
+        at = 0
+        for b, n in enumerate(blocks):
+            rv = ox.default_props(T.eax_reverb, lib=lib, gain_=0.20 + 0.10 * ((b % 4) / 4.0),
+                                  reflections_delay_=(0.012 if b >= 2 else 0.007))
+            eq = ox.default_props(T.equalizer, lib=lib, mid1_gain_=1.0 + 0.5 * ((b % 8) / 8.0))
+            eng.set_effect(3, T.eax_reverb, rv)
+            eng.set_effect(0, T.equalizer, eq)
+            script += [("props", 3, rv), ("props", 0, eq), ("apply",), ("mix", n)]
+            y[:, at:at + n] = eng.mix(np.ascontiguousarray(x[:, at:at + n]))
+            at += n
+    for s in (0, 31, 32, 100, 159, 160, S - 1):
+        expect = H.run_script_orc(checker, F.stereo, 48000, 4, script, x[s])
+        _assert_match(expect, y[s], True, f"{family} stream {s}")
+
+
 def test_full_size_chain_device_buffers(checker):
     """BASELINE cfg4 at full size on one GPU: 65 536 stereo streams, 4-slot chain, device-resident
     buffers.  Size-independent properties: (1) streams fed identical input produce identical output
