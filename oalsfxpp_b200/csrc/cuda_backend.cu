@@ -181,7 +181,7 @@ public:
 #undef OALSFX_QX
 #define OALSFX_DX(id, CT, F0, F1, F2, F3, twin) \
 		case id: \
-			prefer_shared(id, duo::duo_kernel<CT, F0, F1, F2, F3>, 62); \
+			prefer_shared(id, duo::duo_kernel<CT, F0, F1, F2, F3>, 50); \
 			duo::duo_kernel<CT, F0, F1, F2, F3><<<static_cast<unsigned>(args.tile_count), 64, tune_dyn_smem_, st>>>(args); break;
 			OALSFX_DUO_TABLE(OALSFX_DX)
 #undef OALSFX_DX
@@ -198,11 +198,11 @@ public:
 		return check(cudaGetLastError(), kernel_name(kernel_id));
 	}
 
-	// The duo kernels stream through per-warp shared-memory windows (~30 KB per CTA) AND lean on L1:
-	// the stream-major I/O rows are read and written 4 bytes per lane per frame, so each 128-byte line is
-	// touched by 16 consecutive frames.  Measured on B200 (gpurun_out/exp13, 65 536 streams): carve-out
-	// 58-66 % (4 CTAs per SM, ~80-96 KB of L1) 3.14 ms; 72-84 % (5 CTAs) 3.38 ms; 100 % (6 CTAs, ~28 KB
-	// of L1) 3.80 ms; 50 % (3 CTAs) 3.22 ms.
+	// The duo kernels stream through per-warp shared-memory windows (~25 KB per CTA) AND lean on L1:
+	// the stream-major input rows are read 4 bytes per lane per frame, so each 128-byte line serves 16
+	// consecutive frames from L1.  Measured on B200 (gpurun_out/exp13, exp21; 65 536 streams): the optimum
+	// is 4 CTAs per SM with the rest of the 228 KB as L1 (carve-out 46-54 %: 3.07 ms); 5 CTAs (62-80 %) 3.23 ms;
+	// 6 CTAs / ~28 KB of L1 (100 %) 3.8 ms; 3 CTAs 3.2 ms.
 	template <class K> void prefer_shared(int id, K kernel, int default_carveout)
 	{
 		if (!carveout_done_[id]) {

@@ -110,7 +110,6 @@ __global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(
 	// moved with two 16-byte accesses per hand-off instead of eight scattered 4-byte ones (which lean on
 	// L1 to merge 16 frames per line and reach L2 as partial-sector writes).
 	static_assert(kDuoChunk == 4, "the row-batched I/O path moves 4 frames per hand-off");
-	__shared__ float xin[kDuoChunk][CT][kLanes];        // front warp: the current hand-off's input frames
 // Measured (gpurun_out/exp15): batching the OUTPUT rows helps (5 CTAs/SM: 3.38 -> 3.19 ms); batching the
 // INPUT rows hurts (3.17 -> 3.7 ms): 4-byte requests let L1 fetch each 128-byte row segment from DRAM once
 // and serve 16 frames from it, 16-byte requests fetch it as four separate sectors 4 frames apart.
@@ -120,6 +119,7 @@ __global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(
 #ifndef OALSFX_DUO_FAST_OUT
 #define OALSFX_DUO_FAST_OUT 1
 #endif
+	__shared__ float xin[OALSFX_DUO_FAST_IN ? kDuoChunk : 1][CT][kLanes]; // front warp: the current hand-off's input frames
 	const bool fast_rows = CT == 2 && a.io_cs == 1 && a.io_fs == CT && (a.frames % kDuoChunk) == 0 && (a.io_ls % 4) == 0 &&
 		(a.io_ts % 4) == 0 && ((reinterpret_cast<unsigned long long>(a.src) | reinterpret_cast<unsigned long long>(a.dst)) & 15ULL) == 0;
 	const bool fast_io = fast_rows && OALSFX_DUO_FAST_IN;   // input side
@@ -185,14 +185,15 @@ __global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(
 					nx0 = __ldcs(row);
 					nx1 = __ldcs(row + 1);
 				}
+				constexpr int kIn = OALSFX_DUO_FAST_IN ? 1 : 0; // (row index folded to 0 when the path is compiled out)
 				xin[0][0][lane] = c0.x;
 				xin[0][1 % CT][lane] = c0.y;
-				xin[1][0][lane] = c0.z;
-				xin[1][1 % CT][lane] = c0.w;
-				xin[2][0][lane] = c1.x;
-				xin[2][1 % CT][lane] = c1.y;
-				xin[3][0][lane] = c1.z;
-				xin[3][1 % CT][lane] = c1.w;
+				xin[1 * kIn][0][lane] = c0.z;
+				xin[1 * kIn][1 % CT][lane] = c0.w;
+				xin[2 * kIn][0][lane] = c1.x;
+				xin[2 * kIn][1 % CT][lane] = c1.y;
+				xin[3 * kIn][0][lane] = c1.z;
+				xin[3 * kIn][1 % CT][lane] = c1.w;
 			}
 			bar_sync<kBarEmpty>(b);
 #pragma unroll (kDuoUnroll)
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(
 				cp_async_wait_group<kFwDepth>();
 #pragma unroll
 				for (int c = 0; c < CT; ++c) {
-					x[c] = fast_io ? xin[f][c][lane] : io_ok ? col[(i & (kFwSlots - 1)) * kFwSlotFloats + (4 + c) * kLanes] : 0.0F;
+					x[c] = fast_io ? xin[OALSFX_DUO_FAST_IN ? f : 0][c][lane] : io_ok ? col[(i & (kFwSlots - 1)) * kFwSlotFloats + (4 + c) * kLanes] : 0.0F;
 					acc[c] = 0.0F;
 				}
 				// direct send (oalsfxpp.cpp:2924-2950); gains sanitized by the host

@@ -27,11 +27,19 @@
 namespace oalsfx {
 
 // Prefetch window geometry: [ring position & 7][tap 0..23][lane]; taps = {early, early all-pass,
-// early line, late, late line, late all-pass} x 4 lines.  Two batches of kPfBatch positions: the one
+// early line, late, late line, late all-pass} x 4 lines.  Batches of kPfBatch positions: the one
 // being consumed and the one in flight.
 constexpr int kPfBatch = 4;                 // ring positions per batched copy (32 lanes x 16 B = 4 lines)
-constexpr int kPfSlots = 2 * kPfBatch;      // power of two
-constexpr int kPfDepth = kPfSlots - 1;      // furthest position requested beyond the current one
+#ifndef OALSFX_PF_SLOTS
+#define OALSFX_PF_SLOTS 6
+#endif
+// Window rows (ring positions).  8 = two whole batches, the next one requested when the current one
+// starts.  6 = one and a half: the next batch is requested once two positions of the current one have
+// been consumed (their rows plus the two spare ones receive it), a quarter less shared memory per warp.
+constexpr int kPfSlots = OALSFX_PF_SLOTS;
+static_assert(kPfSlots == 6 || kPfSlots == 8, "window of 6 or 8 ring positions");
+constexpr int kPfIssueAt = (kPfSlots == 8 ? 0 : 2); // position within the batch at which the next batch is requested
+constexpr int kPfDepth = 7;                 // bound on how far beyond the current position a request may reach
 constexpr int kPfTaps = 24;                 // whole effect; a half (FxReverbT<.., EARLY, LATE>) uses 12
 constexpr int kPfWarpFloats = kPfSlots * kPfTaps * kLanes; // 24 KiB per reverb warp
 
@@ -132,6 +140,7 @@ struct FxReverbT {
 	float* pf_col;
 	const float* pf_cur;
 	bool primed, can_pf;
+	int32_t pf_row4;   // window row of the first position of the batch holding the current position
 	bool pan_static;   // this sub-chunk: no gain ramps and every one of the 8 x C pan gains is audible
 
 	unsigned pf_s;     // shared-space address of the warp's window (lane offset removed), device build
@@ -396,12 +405,15 @@ struct FxReverbT {
 	// Request ring positions p4 .. p4+3 (p4 a multiple of kPfBatch) of all 24 taps: lane = s * 8 + q
 	// copies streams 4q .. 4q+3 of position p4 + s, i.e. the warp moves one contiguous 512-byte run
 	// per tap (the rings are line-major: consecutive positions of a line are consecutive 128-byte rows).
-	__device__ __forceinline__ void issue_batch(const ReverbCoef& c, int p4) const
+	// `row0`: window row of position p4; rows wrap modulo kPfSlots.
+	__device__ __forceinline__ void issue_batch(const ReverbCoef& c, int p4, int row0) const
 	{
 		const int lane = threadIdx.x % kLanes;
 		const int q4 = (lane & 7) * 4;
 		const int ps = p4 + (lane >> 3);
-		const unsigned dst = pf_s + static_cast<unsigned>(((ps & (kPfSlots - 1)) * (kTaps * kLanes) + q4) * 4);
+		int row = row0 + (lane >> 3);
+		row = (row >= kPfSlots ? row - kPfSlots : row);
+		const unsigned dst = pf_s + static_cast<unsigned>((row * (kTaps * kLanes) + q4) * 4);
 		const float* src = ring.p - lane + q4;
 		const int len0 = c.mask[0] + 1, len1 = c.mask[1] + 1, len2 = c.mask[2] + 1, len3 = c.mask[3] + 1, len4 = c.mask[4] + 1;
 #pragma unroll
@@ -433,21 +445,44 @@ struct FxReverbT {
 		// The batched copies are a whole-warp affair (a lane fetches other lanes' streams), so the
 		// decision is a vote: every lane of the tile must be in the prefetchable state.
 		if (OALSFX_LIKELY(pf_col != nullptr && __all_sync(0xFFFFFFFFU, can_pf))) {
-			// Invariant while primed: the batch holding `pos` and the one after it have been requested.
-			const bool batch_start = (pos & (kPfBatch - 1)) == 0;
-			if (!primed || batch_start) {
+			// Invariant while primed, at position r of the batch whose first position sits in window row
+			// pf_row4: that batch has landed, and the next one has been requested iff r >= kPfIssueAt.
+			const int r = pos & (kPfBatch - 1);
+			if (!primed) {
 				__syncwarp(); // every lane is done with the window rows about to be overwritten
-				if (!primed) {
-					issue_batch(c, pos & ~(kPfBatch - 1));
-					issue_batch(c, (pos & ~(kPfBatch - 1)) + kPfBatch);
-					primed = true;
+				pf_row4 = 0;
+				issue_batch(c, pos - r, 0);
+				if (kPfSlots == 8) {
+					issue_batch(c, pos - r + kPfBatch, kPfBatch);
+					cp_async_wait_group<1>();
+					__syncwarp();
 				} else {
-					issue_batch(c, pos + kPfBatch);
+					cp_async_wait_group<0>();
+					__syncwarp();
+					if (r >= kPfIssueAt) { // rows 0, 1 are re-used by the next batch: only once this one has landed
+						issue_batch(c, pos - r + kPfBatch, kPfBatch);
+					}
 				}
-				cp_async_wait_group<1>(); // all but the newest batch: the one holding `pos` has landed
-				__syncwarp();             // ... for every lane's share of it
+				primed = true;
+			} else {
+				if (r == 0) {
+					pf_row4 += kPfBatch;
+					pf_row4 = (pf_row4 >= kPfSlots ? pf_row4 - kPfSlots : pf_row4);
+				}
+				if (r == kPfIssueAt) {
+					int next = pf_row4 + kPfBatch;
+					next = (next >= kPfSlots ? next - kPfSlots : next);
+					__syncwarp(); // the rows about to be overwritten have been consumed by every lane
+					issue_batch(c, pos - r + kPfBatch, next);
+				}
+				if (r == 0) {
+					cp_async_wait_group<(kPfIssueAt == 0 ? 1 : 0)>(); // the batch holding `pos` has landed
+					__syncwarp();                                      // ... for every lane's share of it
+				}
 			}
-			pf_cur = pf_col + (pos & (kPfSlots - 1)) * (kTaps * kLanes);
+			int row = pf_row4 + r;
+			row = (row >= kPfSlots ? row - kPfSlots : row);
+			pf_cur = pf_col + row * (kTaps * kLanes);
 			body<CT, true>(c, wet, acc, channels, pos); // branch-free: every read is a shared-memory load
 		} else {
 			primed = false;

@@ -36,7 +36,11 @@ namespace quartet {
 #define OALSFX_QUARTET_MIN_CTAS 4      // resident CTAs per SM the register allocation is sized for (128 regs)
 #endif
 
-constexpr int kQuartetChunk = 4;       // frames per hand-off (= the 4-frame output row batch)
+#ifndef OALSFX_QUARTET_CHUNK
+#define OALSFX_QUARTET_CHUNK 4
+#endif
+constexpr int kQuartetChunk = OALSFX_QUARTET_CHUNK; // frames per hand-off (a multiple of the 4-frame output row batch)
+static_assert(kQuartetChunk % 4 == 0, "output rows are written four frames at a time");
 constexpr int kThreads = 4 * kLanes;
 
 // Named barriers of hand-off H (0: A->B, 1: B->C, 2: C->D): full = 4H + buffer, empty = 4H + 2 + buffer.
@@ -260,8 +264,12 @@ __global__ void __launch_bounds__(kThreads, OALSFX_QUARTET_MIN_CTAS) quartet_ker
 			}
 			if (fast_out && io_ok) {
 				float4* row = reinterpret_cast<float4*>(dst + first * CT);
-				__stcs(row, make_float4(xcd[b][0][0][lane], xcd[b][0][1][lane], xcd[b][1][0][lane], xcd[b][1][1][lane]));
-				__stcs(row + 1, make_float4(xcd[b][2][0][lane], xcd[b][2][1][lane], xcd[b][3][0][lane], xcd[b][3][1][lane]));
+#pragma unroll
+				for (int g = 0; g < kQuartetChunk / 4; ++g) {
+					const int f0 = 4 * g;
+					__stcs(row + 2 * g, make_float4(xcd[b][f0][0][lane], xcd[b][f0][1][lane], xcd[b][f0 + 1][0][lane], xcd[b][f0 + 1][1][lane]));
+					__stcs(row + 2 * g + 1, make_float4(xcd[b][f0 + 2][0][lane], xcd[b][f0 + 2][1][lane], xcd[b][f0 + 3][0][lane], xcd[b][f0 + 3][1][lane]));
+				}
 			}
 			if (ci + 2 < chunks) {
 				signal_empty<2>(b);
