@@ -34,11 +34,12 @@ constexpr int kPfBatch = 4;                 // ring positions per batched copy (
 #define OALSFX_PF_SLOTS 6
 #endif
 // Window rows (ring positions).  8 = two whole batches, the next one requested when the current one
-// starts.  6 = one and a half: the next batch is requested once two positions of the current one have
-// been consumed (their rows plus the two spare ones receive it), a quarter less shared memory per warp.
+// starts.  6 (7) = the next batch is requested once two (one) positions of the current one have been
+// consumed -- their rows plus the spare ones receive it: less shared memory per warp, i.e. more L1,
+// for a shorter lead over the arithmetic.
 constexpr int kPfSlots = OALSFX_PF_SLOTS;
-static_assert(kPfSlots == 6 || kPfSlots == 8, "window of 6 or 8 ring positions");
-constexpr int kPfIssueAt = (kPfSlots == 8 ? 0 : 2); // position within the batch at which the next batch is requested
+static_assert(kPfSlots >= 6 && kPfSlots <= 8, "window of 6, 7 or 8 ring positions");
+constexpr int kPfIssueAt = 8 - kPfSlots;    // position within the batch at which the next batch is requested
 constexpr int kPfDepth = 7;                 // bound on how far beyond the current position a request may reach
 constexpr int kPfTaps = 24;                 // whole effect; a half (FxReverbT<.., EARLY, LATE>) uses 12
 constexpr int kPfWarpFloats = kPfSlots * kPfTaps * kLanes; // 24 KiB per reverb warp
