@@ -86,6 +86,29 @@ int oalsfx_engine_mix(oalsfx_engine* e, int frames, const float* src, float* dst
 int oalsfx_engine_reduce_bus(oalsfx_engine* e, int frames, const float* dst, int layout,
 	float* bus, void* cuda_stream);
 
+/* PCM formats either side of the path (device buffers).  The reference's only
+ * producer and consumer of Api::mix buffers is its WAV demo, and these are its conversions:
+ *   oalsfx_pcm_to_float : bit_depth 8: (u8 - 128) / 128.0f, 16: s16 / 32768.0f  (oalsfxpp_test.cpp:703-740)
+ *   oalsfx_float_to_s16 : each of `rows` buffers of `row_len` samples (one per stream) is peak-normalised the
+ *                         way WavFile::save does it -- scale = 1 / max(max(1, max x), -min(-1, min x)),
+ *                         s16 = (int16)(scale * x * 32767.0f), truncating (oalsfxpp_test.cpp:602-651);
+ *                         row_scale (device, `rows` floats, may be NULL) receives the scales.
+ * They let a caller keep 2-byte samples on the host side of PCIe and in HBM between calls. */
+int oalsfx_pcm_to_float(oalsfx_engine* e, const void* src, int bit_depth, float* dst, long long count,
+	void* cuda_stream);
+int oalsfx_float_to_s16(oalsfx_engine* e, const float* src, int16_t* dst, int rows, long long row_len,
+	float* row_scale, void* cuda_stream);
+
+/* State snapshot / restore (the reference has no counterpart: an Api's delay lines
+ * and filter histories are private).  A snapshot holds every byte the streams carry from one block to the
+ * next (delay-line rings, slot state, send filter histories, pending-update flags) into a HOST buffer of
+ * oalsfx_engine_snapshot_size() bytes; restore puts it back into an engine of identical geometry whose
+ * slots hold the same effect types and properties (the caller's configuration is not part of it).  After
+ * a restore the engine continues bit for bit as the snapshotted one would have.  Both synchronize. */
+long long oalsfx_engine_snapshot_size(const oalsfx_engine* e);
+int oalsfx_engine_snapshot(oalsfx_engine* e, void* dst, size_t bytes);
+int oalsfx_engine_restore(oalsfx_engine* e, const void* src, size_t bytes);
+
 /* Integer state of one stream's slot, for bit-exact checks: out[0]=ring write offset,
  * out[1]=reverb fade_count, out[2]=reverb mod index, out[3]=ring-mod phase index.
  * Unused entries are 0.  Synchronizes the device. */

@@ -40,6 +40,13 @@ public:
 	// bus[frame*C + c] = sum over streams (fixed order: lane-major tree per tile, then tiles).
 	virtual bool reduce_bus(const float* data, long long ts, long long ls, long long fs, long long cs,
 		int num_streams, int frames, int channels, float* bus, void* stream) = 0;
+	// PCM formats either side of the path (the reference's only producer/consumer of
+	// sample buffers, its WAV demo: oalsfxpp_test.cpp:703-740 ingest, :602-651 egress).  Device pointers.
+	//   pcm_to_float : bits = 8  -> (int(u8) - 128) / 128.0f ;  bits = 16 -> s16 / 32768.0f
+	//   float_to_s16 : per row (= one stream's buffer, `row_len` samples): scale = 1 / max(max(1, max x), -min(-1, min x)),
+	//                  out = int16(scale * x * 32767.0f) (truncation); row_scale[row] receives the scale if non-null
+	virtual bool pcm_to_float(const void* src, int bits, float* dst, long long count, void* stream) = 0;
+	virtual bool float_to_s16(const float* src, int16_t* dst, int rows, long long row_len, float* row_scale, void* stream) = 0;
 	virtual bool sync(void* stream) = 0;
 	// Engine-owned streams for overlapping host copies with kernels (host-buffer mix): create /
 	// destroy, and "everything enqueued on `signal` so far happens before what `waiter` gets next".

@@ -58,6 +58,92 @@ __global__ void reduce_bus_kernel(const float* data, long long ts, long long ls,
 	}
 }
 
+// ---- PCM formats either side of the path ---------------------------------------
+// HBM-bound element-wise kernels: 16-byte accesses, grid-stride over a multiple of the SM count.
+__global__ void __launch_bounds__(256) pcm16_to_float_kernel(const int16_t* __restrict__ src, float* __restrict__ dst, long long count)
+{
+	// reference: oalsfxpp_test.cpp:728-733  dst[i] = little(src[i]) / 32768.0F
+	const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+	const long long vec = count / 8;
+	for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < vec; i += stride) {
+		const int4 raw = __ldcs(reinterpret_cast<const int4*>(src) + i);
+		const int w[4] = {raw.x, raw.y, raw.z, raw.w};
+		float o[8];
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			o[2 * k] = static_cast<float>(static_cast<int16_t>(w[k] & 0xFFFF)) / 32768.0F;
+			o[2 * k + 1] = static_cast<float>(static_cast<int16_t>(static_cast<unsigned>(w[k]) >> 16)) / 32768.0F;
+		}
+		float4* out = reinterpret_cast<float4*>(dst) + 2 * i;
+		__stcs(out, make_float4(o[0], o[1], o[2], o[3]));
+		__stcs(out + 1, make_float4(o[4], o[5], o[6], o[7]));
+	}
+	for (long long i = vec * 8 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
+		dst[i] = static_cast<float>(src[i]) / 32768.0F;
+	}
+}
+
+__global__ void __launch_bounds__(256) pcm8_to_float_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, long long count)
+{
+	// reference: oalsfxpp_test.cpp:714-719  dst[i] = (int(src[i]) - 128) / 128.0F
+	const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+	const long long vec = count / 4;
+	for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < vec; i += stride) {
+		const unsigned raw = __ldcs(reinterpret_cast<const unsigned*>(src) + i);
+		float4 o;
+		o.x = static_cast<float>(static_cast<int>(raw & 0xFFU) - 128) / 128.0F;
+		o.y = static_cast<float>(static_cast<int>((raw >> 8) & 0xFFU) - 128) / 128.0F;
+		o.z = static_cast<float>(static_cast<int>((raw >> 16) & 0xFFU) - 128) / 128.0F;
+		o.w = static_cast<float>(static_cast<int>(raw >> 24) - 128) / 128.0F;
+		__stcs(reinterpret_cast<float4*>(dst) + i, o);
+	}
+	for (long long i = vec * 4 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
+		dst[i] = static_cast<float>(static_cast<int>(src[i]) - 128) / 128.0F;
+	}
+}
+
+// One CTA per row (= one stream's buffer).  Pass 1: min / max of the row (the reference's scan,
+// oalsfxpp_test.cpp:605-620: min starts at -1, max at +1; min and max are order-independent).  Pass 2:
+// dst = int16(scale * x * 32767.0F), scale = 1 / max(max, -min) (oalsfxpp_test.cpp:622-640).  The second
+// pass re-reads the row from L2 when it fits.
+__global__ void __launch_bounds__(256) float_to_s16_kernel(const float* __restrict__ src, int16_t* __restrict__ dst, long long row_len,
+	float* __restrict__ row_scale)
+{
+	__shared__ float lo_s[8], hi_s[8];
+	const float* row = src + static_cast<long long>(blockIdx.x) * row_len;
+	int16_t* out = dst + static_cast<long long>(blockIdx.x) * row_len;
+	float lo = -1.0F, hi = 1.0F;
+	for (long long i = threadIdx.x; i < row_len; i += blockDim.x) {
+		const float v = row[i];
+		lo = fminf(lo, v);
+		hi = fmaxf(hi, v);
+	}
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) {
+		lo = fminf(lo, __shfl_xor_sync(0xFFFFFFFFU, lo, d));
+		hi = fmaxf(hi, __shfl_xor_sync(0xFFFFFFFFU, hi, d));
+	}
+	if ((threadIdx.x & 31) == 0) {
+		lo_s[threadIdx.x >> 5] = lo;
+		hi_s[threadIdx.x >> 5] = hi;
+	}
+	__syncthreads();
+	lo = lo_s[0];
+	hi = hi_s[0];
+#pragma unroll
+	for (int w = 1; w < 8; ++w) {
+		lo = fminf(lo, lo_s[w]);
+		hi = fmaxf(hi, hi_s[w]);
+	}
+	const float scale = 1.0F / fmaxf(hi, -lo);
+	if (threadIdx.x == 0 && row_scale) {
+		row_scale[blockIdx.x] = scale;
+	}
+	for (long long i = threadIdx.x; i < row_len; i += blockDim.x) {
+		out[i] = static_cast<int16_t>(scale * row[i] * 32767.0F);
+	}
+}
+
 class CudaBackend final : public Backend {
 public:
 	explicit CudaBackend(int device) : device_(device) {}
@@ -232,6 +318,42 @@ public:
 		reduce_bus_kernel<<<static_cast<unsigned>(frames * channels), 256, 0, static_cast<cudaStream_t>(stream)>>>(
 			data, ts, ls, fs, cs, num_streams, channels, bus);
 		return check(cudaGetLastError(), "reduce_bus_kernel");
+	}
+
+	bool pcm_to_float(const void* src, int bits, float* dst, long long count, void* stream) override
+	{
+		if (!bind()) {
+			return false;
+		}
+		if (count <= 0) {
+			return true;
+		}
+		int sms = 148;
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_);
+		const long long want = (count / 8 + 255) / 256;
+		const unsigned blocks = static_cast<unsigned>(want < 1 ? 1 : want > 8LL * sms ? 8LL * sms : want);
+		cudaStream_t st = static_cast<cudaStream_t>(stream);
+		if (bits == 16) {
+			pcm16_to_float_kernel<<<blocks, 256, 0, st>>>(static_cast<const int16_t*>(src), dst, count);
+		} else if (bits == 8) {
+			pcm8_to_float_kernel<<<blocks, 256, 0, st>>>(static_cast<const uint8_t*>(src), dst, count);
+		} else {
+			error_ = "Invalid bit depth."; // the reference's message (oalsfxpp_test.cpp:738)
+			return false;
+		}
+		return check(cudaGetLastError(), "pcm_to_float");
+	}
+
+	bool float_to_s16(const float* src, int16_t* dst, int rows, long long row_len, float* row_scale, void* stream) override
+	{
+		if (!bind()) {
+			return false;
+		}
+		if (rows <= 0 || row_len <= 0) {
+			return true;
+		}
+		float_to_s16_kernel<<<static_cast<unsigned>(rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, row_len, row_scale);
+		return check(cudaGetLastError(), "float_to_s16");
 	}
 
 	bool sync(void* stream) override

@@ -860,6 +860,152 @@ int oalsfx_engine_reduce_bus(oalsfx_engine* e, int frames, const float* dst, int
 	return OALSFX_OK;
 }
 
+int oalsfx_pcm_to_float(oalsfx_engine* e, const void* src, int bit_depth, float* dst, long long count, void* cuda_stream)
+{
+	if (!e || !src || !dst || count < 0) {
+		return e ? e->fail(OALSFX_ERR_ARGUMENT, "Bad pcm_to_float arguments.") : OALSFX_ERR_ARGUMENT;
+	}
+	if (bit_depth != 8 && bit_depth != 16) {
+		return e->fail(OALSFX_ERR_ARGUMENT, "Invalid bit depth."); // reference: oalsfxpp_test.cpp:738
+	}
+	++e->launches;
+	if (!e->be->pcm_to_float(src, bit_depth, dst, count, cuda_stream)) {
+		return e->fail(OALSFX_ERR_DEVICE, e->be->error());
+	}
+	return OALSFX_OK;
+}
+
+int oalsfx_float_to_s16(oalsfx_engine* e, const float* src, int16_t* dst, int rows, long long row_len, float* row_scale,
+	void* cuda_stream)
+{
+	if (!e || !src || !dst || rows < 0 || row_len < 0) {
+		return e ? e->fail(OALSFX_ERR_ARGUMENT, "Bad float_to_s16 arguments.") : OALSFX_ERR_ARGUMENT;
+	}
+	++e->launches;
+	if (!e->be->float_to_s16(src, dst, rows, row_len, row_scale, cuda_stream)) {
+		return e->fail(OALSFX_ERR_DEVICE, e->be->error());
+	}
+	return OALSFX_OK;
+}
+
+// ---- state snapshot / restore --------------------------------------------------
+// Everything a stream carries from one block to the next lives in three kinds of device arenas (delay-line
+// rings and slot state per slot, send filter history) plus one host byte per stream (pending `update`
+// bits).  A snapshot is those bytes behind a header that pins the geometry.
+namespace {
+struct SnapshotHeader {
+	uint32_t magic, version;
+	int32_t streams, tiles, channels, slots, rate, format;
+	int32_t ring_cap[kMaxSlots];
+	uint64_t total_bytes;
+};
+constexpr uint32_t kSnapshotMagic = 0x58464C4FU; // "OLFX"
+
+void snapshot_header(const oalsfx_engine* e, SnapshotHeader& h)
+{
+	std::memset(&h, 0, sizeof(h));
+	h.magic = kSnapshotMagic;
+	h.version = 1;
+	h.streams = e->streams;
+	h.tiles = e->tiles;
+	h.channels = e->channels;
+	h.slots = e->slots;
+	h.rate = e->desc.sampling_rate;
+	h.format = e->desc.channel_format;
+	uint64_t bytes = sizeof(SnapshotHeader) + static_cast<uint64_t>(e->streams);
+	for (int s = 0; s < kMaxSlots; ++s) {
+		h.ring_cap[s] = (s < e->slots ? e->ring_cap[s] : 0);
+		if (s < e->slots) {
+			bytes += static_cast<uint64_t>(e->tiles) * static_cast<uint64_t>(h.ring_cap[s]) * kLanes * sizeof(float);
+			bytes += static_cast<uint64_t>(e->tiles) * kSlotStateWords * kLanes * sizeof(uint32_t);
+		}
+	}
+	bytes += static_cast<uint64_t>(e->tiles) * kSendStateWords * kLanes * sizeof(uint32_t);
+	h.total_bytes = bytes;
+}
+} // namespace
+
+long long oalsfx_engine_snapshot_size(const oalsfx_engine* e)
+{
+	if (!e) {
+		return 0;
+	}
+	SnapshotHeader h;
+	snapshot_header(e, h);
+	return static_cast<long long>(h.total_bytes);
+}
+
+int oalsfx_engine_snapshot(oalsfx_engine* e, void* dst, size_t bytes)
+{
+	if (!e || !dst) {
+		return e ? e->fail(OALSFX_ERR_ARGUMENT, "Bad snapshot arguments.") : OALSFX_ERR_ARGUMENT;
+	}
+	SnapshotHeader h;
+	snapshot_header(e, h);
+	if (bytes < h.total_bytes) {
+		return e->fail(OALSFX_ERR_ARGUMENT, "Snapshot buffer too small.");
+	}
+	if (!e->be->sync(nullptr)) {
+		return e->fail(OALSFX_ERR_DEVICE, e->be->error());
+	}
+	char* out = static_cast<char*>(dst);
+	std::memcpy(out, &h, sizeof(h));
+	out += sizeof(h);
+	std::memcpy(out, e->pending.data(), static_cast<size_t>(e->streams));
+	out += e->streams;
+	bool ok = true;
+	for (int s = 0; s < e->slots && ok; ++s) {
+		const size_t ring_bytes = static_cast<size_t>(e->tiles) * static_cast<size_t>(e->ring_cap[s]) * kLanes * sizeof(float);
+		const size_t state_bytes = static_cast<size_t>(e->tiles) * kSlotStateWords * kLanes * sizeof(uint32_t);
+		if (ring_bytes) {
+			ok = e->be->download(out, e->ring[s], ring_bytes, nullptr);
+			out += ring_bytes;
+		}
+		ok = ok && e->be->download(out, e->slot_state[s], state_bytes, nullptr);
+		out += state_bytes;
+	}
+	ok = ok && e->be->download(out, e->send_state, static_cast<size_t>(e->tiles) * kSendStateWords * kLanes * sizeof(uint32_t), nullptr);
+	ok = ok && e->be->sync(nullptr);
+	return ok ? OALSFX_OK : e->fail(OALSFX_ERR_DEVICE, e->be->error());
+}
+
+int oalsfx_engine_restore(oalsfx_engine* e, const void* src, size_t bytes)
+{
+	if (!e || !src || bytes < sizeof(SnapshotHeader)) {
+		return e ? e->fail(OALSFX_ERR_ARGUMENT, "Bad restore arguments.") : OALSFX_ERR_ARGUMENT;
+	}
+	SnapshotHeader want, got;
+	snapshot_header(e, want);
+	std::memcpy(&got, src, sizeof(got));
+	if (got.magic != kSnapshotMagic || got.version != want.version) {
+		return e->fail(OALSFX_ERR_ARGUMENT, "Not an engine snapshot.");
+	}
+	if (std::memcmp(&got, &want, sizeof(got)) != 0 || bytes < got.total_bytes) {
+		return e->fail(OALSFX_ERR_ARGUMENT, "Snapshot does not match this engine (streams, format, rate, slots or effect types differ).");
+	}
+	if (!e->be->sync(nullptr)) {
+		return e->fail(OALSFX_ERR_DEVICE, e->be->error());
+	}
+	const char* in = static_cast<const char*>(src) + sizeof(SnapshotHeader);
+	std::memcpy(e->pending.data(), in, static_cast<size_t>(e->streams));
+	in += e->streams;
+	e->groups_dirty = true;
+	bool ok = true;
+	for (int s = 0; s < e->slots && ok; ++s) {
+		const size_t ring_bytes = static_cast<size_t>(e->tiles) * static_cast<size_t>(e->ring_cap[s]) * kLanes * sizeof(float);
+		const size_t state_bytes = static_cast<size_t>(e->tiles) * kSlotStateWords * kLanes * sizeof(uint32_t);
+		if (ring_bytes) {
+			ok = e->be->upload(e->ring[s], in, ring_bytes, nullptr);
+			in += ring_bytes;
+		}
+		ok = ok && e->be->upload(e->slot_state[s], in, state_bytes, nullptr);
+		in += state_bytes;
+	}
+	ok = ok && e->be->upload(e->send_state, in, static_cast<size_t>(e->tiles) * kSendStateWords * kLanes * sizeof(uint32_t), nullptr);
+	ok = ok && e->be->sync(nullptr);
+	return ok ? OALSFX_OK : e->fail(OALSFX_ERR_DEVICE, e->be->error());
+}
+
 int oalsfx_engine_debug_state(oalsfx_engine* e, int stream, int slot, int32_t out[4])
 {
 	if (!e || !out || stream < 0 || stream >= e->streams || slot < 0 || slot >= e->slots) {

@@ -73,6 +73,16 @@ def bind(lib):
     lib.oalsfx_reverb_preset.restype = i32
     lib.oalsfx_reverb_preset_name.argtypes = [i32]
     lib.oalsfx_reverb_preset_name.restype = C.c_char_p
+    lib.oalsfx_pcm_to_float.argtypes = [vp, vp, i32, vp, C.c_longlong, vp]
+    lib.oalsfx_pcm_to_float.restype = i32
+    lib.oalsfx_float_to_s16.argtypes = [vp, vp, vp, i32, C.c_longlong, vp, vp]
+    lib.oalsfx_float_to_s16.restype = i32
+    lib.oalsfx_engine_snapshot_size.argtypes = [vp]
+    lib.oalsfx_engine_snapshot_size.restype = C.c_longlong
+    lib.oalsfx_engine_snapshot.argtypes = [vp, vp, C.c_size_t]
+    lib.oalsfx_engine_snapshot.restype = i32
+    lib.oalsfx_engine_restore.argtypes = [vp, vp, C.c_size_t]
+    lib.oalsfx_engine_restore.restype = i32
     return lib
 
 
@@ -81,7 +91,8 @@ EXPORTED_SYMBOLS = (
     "oalsfx_engine_set_sends", "oalsfx_engine_mix", "oalsfx_engine_reduce_bus",
     "oalsfx_engine_debug_state", "oalsfx_engine_launch_count", "oalsfx_engine_device_bytes",
     "oalsfx_last_error", "oalsfx_build_info", "oalsfx_effect_defaults", "oalsfx_effect_normalize",
-    "oalsfx_reverb_preset", "oalsfx_reverb_preset_name",
+    "oalsfx_reverb_preset", "oalsfx_reverb_preset_name", "oalsfx_pcm_to_float", "oalsfx_float_to_s16",
+    "oalsfx_engine_snapshot_size", "oalsfx_engine_snapshot", "oalsfx_engine_restore",
 )
 
 _LIB = None
@@ -202,6 +213,29 @@ class Engine:
         out = (C.c_int32 * 4)()
         self._check(self.lib.oalsfx_engine_debug_state(self._h, stream, slot, out))
         return {"offset": out[0], "fade_count": out[1], "mod_index": out[2], "ring_mod_index": out[3]}
+
+    def pcm_to_float(self, src, bit_depth, dst, count, stream=0):
+        """8/16-bit PCM -> float on device buffers (the reference demo's ingest, oalsfxpp_test.cpp:703-740)."""
+        self._check(self.lib.oalsfx_pcm_to_float(self._h, _ptr(src), int(bit_depth), _ptr(dst), int(count),
+                                                 C.c_void_p(stream)))
+        return dst
+
+    def float_to_s16(self, src, dst, rows, row_len, row_scale=None, stream=0):
+        """float -> peak-normalised s16 per row on device buffers (the demo's egress, oalsfxpp_test.cpp:602-651)."""
+        self._check(self.lib.oalsfx_float_to_s16(self._h, _ptr(src), _ptr(dst), int(rows), int(row_len),
+                                                 _ptr(row_scale) if row_scale is not None else None, C.c_void_p(stream)))
+        return dst
+
+    def snapshot(self):
+        """All stream state (delay lines, filter histories, pending flags) as one host byte array."""
+        size = int(self.lib.oalsfx_engine_snapshot_size(self._h))
+        buf = np.empty(size, dtype=np.uint8)
+        self._check(self.lib.oalsfx_engine_snapshot(self._h, buf.ctypes.data, size))
+        return buf
+
+    def restore(self, snapshot):
+        snapshot = np.ascontiguousarray(snapshot, dtype=np.uint8)
+        self._check(self.lib.oalsfx_engine_restore(self._h, snapshot.ctypes.data, snapshot.size))
 
     @property
     def launch_count(self):

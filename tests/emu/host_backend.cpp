@@ -6,6 +6,7 @@
 // oracle in a container without a GPU.  It is built into tests/_build/liboalsfx_emu.so by
 // tests/emu/Makefile, is never part of the package and is not a fallback: liboalsfx_b200.so links
 // cuda_backend.cu only and refuses to create an engine without a CUDA device.
+#include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -85,6 +86,37 @@ public:
 					sum += data[(s / kLanes) * ts + (s % kLanes) * ls + f * fs + c * cs];
 				}
 				bus[f * channels + c] = static_cast<float>(sum);
+			}
+		}
+		return true;
+	}
+	bool pcm_to_float(const void* src, int bits, float* dst, long long count, void*) override
+	{
+		if (bits != 8 && bits != 16) {
+			error_ = "Invalid bit depth.";
+			return false;
+		}
+		for (long long i = 0; i < count; ++i) {
+			dst[i] = bits == 16 ? static_cast<float>(static_cast<const int16_t*>(src)[i]) / 32768.0F :
+				static_cast<float>(static_cast<int>(static_cast<const uint8_t*>(src)[i]) - 128) / 128.0F;
+		}
+		return true;
+	}
+	bool float_to_s16(const float* src, int16_t* dst, int rows, long long row_len, float* row_scale, void*) override
+	{
+		for (int r = 0; r < rows; ++r) {
+			const float* row = src + static_cast<long long>(r) * row_len;
+			float lo = -1.0F, hi = 1.0F;
+			for (long long i = 0; i < row_len; ++i) {
+				lo = row[i] < lo ? row[i] : lo;
+				hi = row[i] > hi ? row[i] : hi;
+			}
+			const float scale = 1.0F / (hi > -lo ? hi : -lo);
+			if (row_scale) {
+				row_scale[r] = scale;
+			}
+			for (long long i = 0; i < row_len; ++i) {
+				dst[static_cast<long long>(r) * row_len + i] = static_cast<int16_t>(scale * row[i] * 32767.0F);
 			}
 		}
 		return true;

@@ -10,7 +10,7 @@ from oalsfxpp_b200 import engine as E
 def _declared_symbols():
     text = open(os.path.join(H.ROOT, "include", "oalsfx_engine.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(oalsfx_[a-z_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(oalsfx_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_header_symbols_match_binding_list():
