@@ -1,0 +1,78 @@
+#!/usr/bin/env python3
+"""Secondary measurements: ms per 1024-frame block of every BASELINE.json configuration on ONE GPU,
+device-resident buffers, CUDA events on the launching stream (the headline cfg4 line is bench.py's).
+
+    python profiles/cfg_timings.py > profiles/r01_cfg_timings.json
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import oalsfxpp_b200 as ox  # noqa: E402
+from oalsfxpp_b200 import ChannelFormat as F, EffectType as T  # noqa: E402
+
+BLOCK = 1024
+
+
+def run(name, streams, fmt, rate, chain, bytes_per_frame, schedule=None, blocks=24, warm=4):
+    channels = ox.channel_count(fmt)
+    dev = torch.device("cuda:0")
+    x = (torch.rand(streams, BLOCK, channels, device=dev) - 0.5)
+    y = torch.empty_like(x)
+    stream = torch.cuda.current_stream().cuda_stream
+    with ox.Engine(streams, fmt, rate, len(chain)) as eng:
+        for i, t in enumerate(chain):
+            eng.set_effect(i, t)
+        host_s = 0.0
+        times = []
+        for b in range(warm + blocks):
+            t0 = time.perf_counter()
+            if schedule:
+                schedule(eng, b)
+            t1 = time.perf_counter()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            eng.mix(x, y, frames=BLOCK, stream=stream)
+            e1.record()
+            torch.cuda.synchronize()
+            if b >= warm:
+                host_s += t1 - t0
+                times.append(e0.elapsed_time(e1))
+        launches = eng.launch_count
+    ms = float(np.median(times))
+    frames = streams * BLOCK
+    return {"config": name, "streams": streams, "channels": channels, "rate": rate, "ms_per_block_device": ms,
+            "host_param_update_ms_per_block": host_s / blocks * 1e3,
+            "channel_samples_per_s": frames * channels / (ms * 1e-3),
+            "algorithmic_GBps": bytes_per_frame * frames / (ms * 1e-3) / 1e9, "launches": launches}
+
+
+def cfg2_schedule(eng, b):
+    rv = ox.default_props(T.eax_reverb, gain_=0.20 + 0.10 * ((b % 4) / 4.0), reflections_delay_=(0.012 if (b // 16) % 2 else 0.007))
+    eq = ox.default_props(T.equalizer, mid1_gain_=1.0 + 0.5 * ((b % 8) / 8.0))
+    eng.set_effect(3, T.eax_reverb, rv)
+    eng.set_effect(0, T.equalizer, eq)
+
+
+def main():
+    out = [
+        run("cfg1: EAX reverb, 1024 mono streams", 1024, F.mono, 48000, [T.eax_reverb], 200),
+        run("cfg2: EQ+chorus+echo+EAX, 4096 stereo streams, per-block parameter changes", 4096, F.stereo, 48000,
+            [T.equalizer, T.chorus, T.echo, T.eax_reverb], 236, schedule=cfg2_schedule, blocks=48),
+        run("cfg2 without parameter changes", 4096, F.stereo, 48000, [T.equalizer, T.chorus, T.echo, T.eax_reverb], 236),
+        run("cfg3: flanger+ring modulator+distortion+compressor, 16384 mono streams @96 kHz", 16384, F.mono, 96000,
+            [T.flanger, T.ring_modulator, T.distortion, T.compressor], 24),
+        run("cfg4: EQ+chorus+echo+EAX, 65536 stereo streams", 65536, F.stereo, 48000,
+            [T.equalizer, T.chorus, T.echo, T.eax_reverb], 236, blocks=10, warm=3),
+    ]
+    print(json.dumps({"gpu": torch.cuda.get_device_name(0), "block_frames": BLOCK, "results": out}, indent=1))
+
+
+if __name__ == "__main__":
+    main()
