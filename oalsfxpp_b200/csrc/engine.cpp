@@ -100,9 +100,10 @@ struct oalsfx_engine {
 	std::vector<Group> groups;
 	bool groups_dirty = true;
 	long long launches = 0;
-	// Which fused kernel family serves whole-tile groups: 2 = duo (default, the fastest measured),
-	// 3 = quartet (four-stage pipeline; falls back to duo for signatures without a quartet entry),
-	// 1 = quad, 0 = the plain thread-per-stream twin.  OALSFX_KERNEL=duo|quartet|quad|single overrides
+	// Which fused kernel family serves whole-tile groups: 2 = automatic (default): the two-stage duo kernel,
+	// or the four-stage quartet pipeline when the group has too few tiles to fill the GPU (and for
+	// signatures that only have a quartet entry); 3 = quartet wherever it exists; 4 = duo wherever it exists;
+	// 1 = quad, 0 = the plain thread-per-stream twin.  OALSFX_KERNEL=auto|quartet|duo|quad|single overrides
 	// (A/B measurements and the parity tests of every family).
 	int family = 2;
 	// Host-buffer mix: tile slice the next launches are restricted to (0 = all tiles), and the
@@ -513,10 +514,17 @@ struct oalsfx_engine {
 			sanitize_gains(a);
 			const bool whole_tiles = g.identity || g.full_tiles;
 			int id = ki.id;
-			if (whole_tiles && family == 3 && quartet_for_twin(ki.id) >= 0) {
+			// Few tiles cannot fill the GPU with two warps each: below ~one tile per SM the four-stage pipeline
+			// (twice the warps per tile) wins -- measured on B200, 4-slot stereo chain, ms per 1024-frame block:
+			// 128 tiles 0.47 (quartet) vs 0.63 (duo); 256 tiles 0.64 vs 0.64; 2048 tiles 3.6 vs 3.07.
+			constexpr int kPipelineMaxTiles = 160;
+			const bool few_tiles = a.tile_count <= kPipelineMaxTiles;
+			if (whole_tiles && (family == 3 || (family == 2 && few_tiles)) && quartet_for_twin(ki.id) >= 0) {
 				id = quartet_for_twin(ki.id);
 			} else if (whole_tiles && family >= 2 && duo_for_twin(ki.id) >= 0) {
 				id = duo_for_twin(ki.id);
+			} else if (whole_tiles && family >= 2 && quartet_for_twin(ki.id) >= 0) {
+				id = quartet_for_twin(ki.id); // no duo entry for this signature (single reverb slot)
 			} else if (whole_tiles && family >= 1 && quad_for_twin(ki.id) >= 0) {
 				id = quad_for_twin(ki.id);
 			}
@@ -592,7 +600,7 @@ int oalsfx_engine_create(const oalsfx_engine_desc* desc, oalsfx_engine** out)
 	e->channels = dev.channels;
 	e->slots = desc->effect_count;
 	if (const char* fam = std::getenv("OALSFX_KERNEL")) {
-		e->family = (std::strcmp(fam, "single") == 0 ? 0 : std::strcmp(fam, "quad") == 0 ? 1 : std::strcmp(fam, "quartet") == 0 ? 3 : 2);
+		e->family = (std::strcmp(fam, "single") == 0 ? 0 : std::strcmp(fam, "quad") == 0 ? 1 : std::strcmp(fam, "quartet") == 0 ? 3 : std::strcmp(fam, "duo") == 0 ? 4 : 2);
 	}
 	e->be = make_backend(desc->device, g_create_error);
 	if (!e->be) {

@@ -50,7 +50,9 @@
 // Quartet kernels (quartet.cuh: four pipeline stages per tile -- dry + slot 0 | slots 1, 2 + reverb input |
 // reverb early half | reverb late half + output).  TX(id, CT, F0, F1, F2, F3, twin), same twin rule.
 #define OALSFX_QUARTET_TABLE(TX) \
-	TX(kQuartetChainStereo, 2, FxEqualizer, FxModDelay, FxEcho, FxReverb, kChainStereo)
+	TX(kQuartetChainStereo, 2, FxEqualizer, FxModDelay, FxEcho, FxReverb, kChainStereo) \
+	/* cfg1: one (EAX) reverb slot, mono: few streams, latency-bound -- more warps per tile is the lever */ \
+	TX(kQuartetReverbMono, 1, FxReverb, FxNull, FxNull, FxNull, kReverbMono)
 
 namespace oalsfx {
 

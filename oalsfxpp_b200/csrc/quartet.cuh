@@ -53,8 +53,16 @@ template <int H> __device__ __forceinline__ void signal_empty(int b) { duo::bar_
 template <int CT, class F0, class F1, class F2, class F3>
 __global__ void __launch_bounds__(kThreads, OALSFX_QUARTET_MIN_CTAS) quartet_kernel(const __grid_constant__ MixArgs a)
 {
-	static_assert(std::is_same<F3, FxReverb>::value, "the quartet pipeline splits a reverb in slot 3");
-	static_assert(CT == 2, "the output row batch assumes stereo");
+	// RP: position of the reverb the pipeline is built around -- the LAST non-null slot, so that the stages'
+	// order (slots before it in A and B, its halves in C and D) is also the reference's summation order.
+	constexpr int RP = std::is_same<F3, FxReverb>::value ? 3 : std::is_same<F2, FxReverb>::value ? 2 :
+		std::is_same<F1, FxReverb>::value ? 1 : std::is_same<F0, FxReverb>::value ? 0 : -1;
+	static_assert(RP >= 0, "the quartet pipeline splits a reverb");
+	static_assert((RP >= 3 || F3::kIsNull) && (RP >= 2 || F2::kIsNull) && (RP >= 1 || F1::kIsNull), "slots after the reverb must be empty");
+	static_assert(CT == 1 || CT == 2, "output rows are batched for mono and stereo");
+	using A0 = typename std::conditional<(RP > 0), F0, FxNull>::type;   // stage A: slot 0 unless it is the reverb
+	using B1 = typename std::conditional<(RP > 1), F1, FxNull>::type;   // stage B: slots 1 and 2 if they precede it
+	using B2 = typename std::conditional<(RP > 2), F2, FxNull>::type;
 	__shared__ __align__(16) float win_c[FxReverbEarly::kWindowFloats]; // stage C: 12 early taps x 8 ring positions
 	__shared__ __align__(16) float win_d[FxReverbLate::kWindowFloats];  // stage D: 12 late taps x 8 ring positions
 	__shared__ float xab[2][kQuartetChunk][2 * CT][kLanes];              // A -> B: x_0..x_C-1, bus_0..bus_C-1
@@ -77,16 +85,16 @@ __global__ void __launch_bounds__(kThreads, OALSFX_QUARTET_MIN_CTAS) quartet_ker
 	float* dst = a.dst + tile * a.io_ts + lane * a.io_ls;
 	uint32_t* ss = a.send_state + (static_cast<long long>(tile) * kSendStateWords) * kLanes + lane;
 	const int chunks = (a.frames + kQuartetChunk - 1) / kQuartetChunk;
-	// Output rows: with interleaved frames a thread's 4 frames x 2 channels are one 32-byte sector of its row.
+	// Output rows: with interleaved frames a thread's 4 frames x CT channels are 16 or 32 contiguous bytes of its row.
 	const bool fast_out = a.io_cs == 1 && a.io_fs == CT && (a.frames % kQuartetChunk) == 0 && (a.io_ls % 4) == 0 &&
 		(a.io_ts % 4) == 0 && (reinterpret_cast<unsigned long long>(a.dst) & 15ULL) == 0;
 
 	if (stage == 0) {
 		// ---- A: input, dry, slot 0 ----
-		SlotRunner<CT, false, F0> r0;
+		SlotRunner<CT, false, A0> r0;
 		SlotRunner<CT, false, FxReverbInput> r3in; // adds nothing to the bus, so it may run ahead of slots 1 and 2
 		r0.begin(a, 0, tile, lane, nullptr);
-		r3in.begin(a, 3, tile, lane, nullptr);
+		r3in.begin(a, RP, tile, lane, nullptr);
 		const unsigned win_s = smem_addr(&win_a[0][0][lane]);
 		const float* in = src;
 		auto issue_input = [&](int frame) {
@@ -124,7 +132,7 @@ __global__ void __launch_bounds__(kThreads, OALSFX_QUARTET_MIN_CTAS) quartet_ker
 					pan_add<CT, true>(acc, CT, a.direct.gains[c], x[c]);
 				}
 				r0.step(a, 0, x, acc);
-				r3in.step(a, 3, x, acc);
+				r3in.step(a, RP, x, acc);
 #pragma unroll
 				for (int c = 0; c < CT; ++c) {
 					xab[b][f][c][lane] = x[c];
@@ -136,18 +144,19 @@ __global__ void __launch_bounds__(kThreads, OALSFX_QUARTET_MIN_CTAS) quartet_ker
 		}
 		cp_async_wait_group<0>();
 		r0.end_state_only(a, 0, tile, lane);
-		r3in.end_state_only(a, 3, tile, lane);
+		r3in.end_state_only(a, RP, tile, lane);
 		duo::store_passthrough_history<CT>(ss, 0, src, a, io_ok);
-		if (!F0::kIsNull) {
+		if (!A0::kIsNull) {
 			duo::store_passthrough_history<CT>(ss, 1 + a.aux_index[0], src, a, io_ok);
 		}
+		duo::store_passthrough_history<CT>(ss, 1 + a.aux_index[RP], src, a, io_ok);
 	} else if (stage == 1) {
 		// ---- B: slots 1, 2 and the reverb's input stage ----
-		SlotRunner<CT, false, F1> r1;
-		SlotRunner<CT, false, F2> r2;
+		SlotRunner<CT, false, B1> r1;
+		SlotRunner<CT, false, B2> r2;
 		// Window taps: 0,1 = the first chorus/flanger, 2,3 = the first echo.
-		constexpr bool m1 = std::is_same<F1, FxModDelay>::value, m2 = std::is_same<F2, FxModDelay>::value && !m1;
-		constexpr bool e1 = std::is_same<F1, FxEcho>::value, e2 = std::is_same<F2, FxEcho>::value && !e1;
+		constexpr bool m1 = std::is_same<B1, FxModDelay>::value, m2 = std::is_same<B2, FxModDelay>::value && !m1;
+		constexpr bool e1 = std::is_same<B1, FxEcho>::value, e2 = std::is_same<B2, FxEcho>::value && !e1;
 		float* col = win_b + lane;
 		r1.begin(a, 1, tile, lane, m1 ? col : e1 ? col + 2 * kLanes : nullptr);
 		r2.begin(a, 2, tile, lane, m2 ? col : e2 ? col + 2 * kLanes : nullptr);
@@ -191,17 +200,16 @@ __global__ void __launch_bounds__(kThreads, OALSFX_QUARTET_MIN_CTAS) quartet_ker
 		cp_async_wait_group<0>();
 		r1.end_state_only(a, 1, tile, lane);
 		r2.end_state_only(a, 2, tile, lane);
-		if (!F1::kIsNull) {
+		if (!B1::kIsNull) {
 			duo::store_passthrough_history<CT>(ss, 1 + a.aux_index[1], src, a, io_ok);
 		}
-		if (!F2::kIsNull) {
+		if (!B2::kIsNull) {
 			duo::store_passthrough_history<CT>(ss, 1 + a.aux_index[2], src, a, io_ok);
 		}
-		duo::store_passthrough_history<CT>(ss, 1 + a.aux_index[3], src, a, io_ok);
 	} else if (stage == 2) {
 		// ---- C: reverb, early half ----
 		SlotRunner<CT, false, FxReverbEarly> r3;
-		r3.begin(a, 3, tile, lane, win_c + lane);
+		r3.begin(a, RP, tile, lane, win_c + lane);
 		signal_empty<1>(0);
 		signal_empty<1>(1);
 		const float none[kWetChannels] = {0.0F, 0.0F, 0.0F, 0.0F};
@@ -217,7 +225,7 @@ __global__ void __launch_bounds__(kThreads, OALSFX_QUARTET_MIN_CTAS) quartet_ker
 				for (int c = 0; c < CT; ++c) {
 					acc[c] = xbc[b][f][c][lane];
 				}
-				r3.fx.template step<CT, true>(a.slot[3], none, acc, CT); // the halves do not read the wet bus
+				r3.fx.template step<CT, true>(a.slot[RP], none, acc, CT); // the halves do not read the wet bus
 #pragma unroll
 				for (int c = 0; c < CT; ++c) {
 					xcd[b][f][c][lane] = acc[c];
@@ -229,11 +237,11 @@ __global__ void __launch_bounds__(kThreads, OALSFX_QUARTET_MIN_CTAS) quartet_ker
 				signal_empty<1>(b);
 			}
 		}
-		r3.end_state_only(a, 3, tile, lane);
+		r3.end_state_only(a, RP, tile, lane);
 	} else {
 		// ---- D: reverb, late half, output ----
 		SlotRunner<CT, false, FxReverbLate> r3;
-		r3.begin(a, 3, tile, lane, win_d + lane);
+		r3.begin(a, RP, tile, lane, win_d + lane);
 		signal_empty<2>(0);
 		signal_empty<2>(1);
 		const float none[kWetChannels] = {0.0F, 0.0F, 0.0F, 0.0F};
@@ -249,7 +257,7 @@ __global__ void __launch_bounds__(kThreads, OALSFX_QUARTET_MIN_CTAS) quartet_ker
 				for (int c = 0; c < CT; ++c) {
 					acc[c] = xcd[b][f][c][lane];
 				}
-				r3.fx.template step<CT, true>(a.slot[3], none, acc, CT);
+				r3.fx.template step<CT, true>(a.slot[RP], none, acc, CT);
 				if (fast_out) {
 #pragma unroll
 					for (int c = 0; c < CT; ++c) {
@@ -263,19 +271,20 @@ __global__ void __launch_bounds__(kThreads, OALSFX_QUARTET_MIN_CTAS) quartet_ker
 				}
 			}
 			if (fast_out && io_ok) {
+				// kQuartetChunk frames x CT channels of this thread's row, 16 bytes at a time
 				float4* row = reinterpret_cast<float4*>(dst + first * CT);
 #pragma unroll
-				for (int g = 0; g < kQuartetChunk / 4; ++g) {
-					const int f0 = 4 * g;
-					__stcs(row + 2 * g, make_float4(xcd[b][f0][0][lane], xcd[b][f0][1][lane], xcd[b][f0 + 1][0][lane], xcd[b][f0 + 1][1][lane]));
-					__stcs(row + 2 * g + 1, make_float4(xcd[b][f0 + 2][0][lane], xcd[b][f0 + 2][1][lane], xcd[b][f0 + 3][0][lane], xcd[b][f0 + 3][1][lane]));
+				for (int g = 0; g < kQuartetChunk * CT / 4; ++g) {
+					const int e0 = 4 * g; // element index within the chunk: frame = e / CT, channel = e % CT
+					__stcs(row + g, make_float4(xcd[b][(e0 + 0) / CT][(e0 + 0) % CT][lane], xcd[b][(e0 + 1) / CT][(e0 + 1) % CT][lane],
+						xcd[b][(e0 + 2) / CT][(e0 + 2) % CT][lane], xcd[b][(e0 + 3) / CT][(e0 + 3) % CT][lane]));
 				}
 			}
 			if (ci + 2 < chunks) {
 				signal_empty<2>(b);
 			}
 		}
-		r3.end_state_only(a, 3, tile, lane);
+		r3.end_state_only(a, RP, tile, lane);
 	}
 }
 

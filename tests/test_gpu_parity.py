@@ -187,6 +187,35 @@ def test_every_kernel_family_on_the_chain(checker, family, monkeypatch):
         _assert_match(expect, y[s], True, f"{family} stream {s}")
 
 
+@pytest.mark.parametrize("family", ["quartet", "quad", "single"])
+def test_every_kernel_family_on_the_single_reverb_slot(checker, family, monkeypatch):
+    """cfg1's signature (one reverb slot, mono): pipeline (default), quad and plain kernels, with a preset
+    change mid-stream (tap cross-fade + gain ramp), a modulated preset and odd block sizes."""
+    monkeypatch.setenv("OALSFX_KERNEL", family)
+    lib = _lib()
+    S = 96
+    blocks = [1024, 512, 1023, 1024, 6]
+    total = sum(blocks)
+    x = np.stack([H.noise(50 + s, 1, total) for s in range(S)])
+    y = np.empty_like(x)
+    presets = [None, ox.reverb_preset("Default", "forest", lib=lib), None,
+               ox.default_props(T.eax_reverb, lib=lib, modulation_depth_=0.8, modulation_time_=0.6), None]
+    script = [("type", 0, T.eax_reverb), ("apply",)]
+    with ox.Engine(S, F.mono, 48000, 1, lib=lib) as eng:
+        eng.set_effect(0, T.eax_reverb)
+        at = 0
+        for n, p in zip(blocks, presets):
+            if p is not None:
+                eng.set_effect(0, T.eax_reverb, p)
+                script += [("props", 0, p), ("apply",)]
+            script += [("mix", n)]
+            y[:, at:at + n] = eng.mix(np.ascontiguousarray(x[:, at:at + n]))
+            at += n
+    for s in (0, 31, 32, 95):
+        expect = H.run_script_orc(checker, F.mono, 48000, 1, script, x[s])
+        _assert_match(expect, y[s], True, f"{family} stream {s}")
+
+
 def test_full_size_chain_device_buffers(checker):
     """BASELINE cfg4 at full size on one GPU: 65 536 stereo streams, 4-slot chain, device-resident
     buffers.  Size-independent properties: (1) streams fed identical input produce identical output
