@@ -34,7 +34,10 @@ namespace duo {
 #endif
 
 constexpr int kDuoUnroll = OALSFX_DUO_UNROLL;
-constexpr int kDuoChunk = 4;           // frames per hand-off
+#ifndef OALSFX_DUO_CHUNK
+#define OALSFX_DUO_CHUNK 4
+#endif
+constexpr int kDuoChunk = OALSFX_DUO_CHUNK; // frames per hand-off (a multiple of the 4-frame output row batch)
 constexpr int kBarFull = 0;            // named barriers 0,1: buffer b filled by the front warp
 constexpr int kBarEmpty = 2;           // named barriers 2,3: buffer b drained by the back warp
 
@@ -109,7 +112,6 @@ __global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(
 	// thread's kDuoChunk = 4 frames x 2 channels are 32 contiguous bytes of its row -- one full sector,
 	// moved with two 16-byte accesses per hand-off instead of eight scattered 4-byte ones (which lean on
 	// L1 to merge 16 frames per line and reach L2 as partial-sector writes).
-	static_assert(kDuoChunk == 4, "the row-batched I/O path moves 4 frames per hand-off");
 // Measured (gpurun_out/exp15): batching the OUTPUT rows helps (5 CTAs/SM: 3.38 -> 3.19 ms); batching the
 // INPUT rows hurts (3.17 -> 3.7 ms): 4-byte requests let L1 fetch each 128-byte row segment from DRAM once
 // and serve 16 frames from it, 16-byte requests fetch it as four separate sectors 4 frames apart.
@@ -119,6 +121,7 @@ __global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(
 #ifndef OALSFX_DUO_FAST_OUT
 #define OALSFX_DUO_FAST_OUT 1
 #endif
+	static_assert(kDuoChunk % 4 == 0 && (kDuoChunk == 4 || !OALSFX_DUO_FAST_IN), "output rows are written four frames at a time");
 	__shared__ float xin[OALSFX_DUO_FAST_IN ? kDuoChunk : 1][CT][kLanes]; // front warp: the current hand-off's input frames
 	const bool fast_rows = CT == 2 && a.io_cs == 1 && a.io_fs == CT && (a.frames % kDuoChunk) == 0 && (a.io_ls % 4) == 0 &&
 		(a.io_ts % 4) == 0 && ((reinterpret_cast<unsigned long long>(a.src) | reinterpret_cast<unsigned long long>(a.dst)) & 15ULL) == 0;
@@ -280,10 +283,14 @@ __global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(
 			}
 			if (fast_out && io_ok) {
 				float4* row = reinterpret_cast<float4*>(dst + first * CT);
-				__stcs(row, make_float4(xch[b][0][kBusAt][lane], xch[b][0][kBusAt + 1 % CT][lane], xch[b][1][kBusAt][lane],
-					xch[b][1][kBusAt + 1 % CT][lane]));
-				__stcs(row + 1, make_float4(xch[b][2][kBusAt][lane], xch[b][2][kBusAt + 1 % CT][lane], xch[b][3][kBusAt][lane],
-					xch[b][3][kBusAt + 1 % CT][lane]));
+#pragma unroll
+				for (int g = 0; g < kDuoChunk / 4; ++g) {
+					const int f0 = 4 * g;
+					__stcs(row + 2 * g, make_float4(xch[b][f0][kBusAt][lane], xch[b][f0][kBusAt + 1 % CT][lane],
+						xch[b][f0 + 1][kBusAt][lane], xch[b][f0 + 1][kBusAt + 1 % CT][lane]));
+					__stcs(row + 2 * g + 1, make_float4(xch[b][f0 + 2][kBusAt][lane], xch[b][f0 + 2][kBusAt + 1 % CT][lane],
+						xch[b][f0 + 3][kBusAt][lane], xch[b][f0 + 3][kBusAt + 1 % CT][lane]));
+				}
 			}
 			if (ci + 2 < chunks) {
 				bar_arrive<kBarEmpty>(b); // nobody waits for the last two drains

@@ -187,6 +187,83 @@ def test_every_kernel_family_on_the_chain(checker, family, monkeypatch):
         _assert_match(expect, y[s], True, f"{family} stream {s}")
 
 
+@pytest.mark.parametrize("variant", ["standard-reverb-96k", "zero-delays", "density-extremes"])
+@pytest.mark.parametrize("family", ["quartet", "duo"])
+def test_pipelined_kernels_on_reverb_corner_cases(checker, family, variant, monkeypatch):
+    """The warp-specialised kernels hand delay-line data from one warp to the next through HBM.  Corner cases
+    of that hand-off: the standard (non-EAX) reverb at 96 kHz (all delays doubled, no high-pass stage);
+    reflections_delay = late_reverb_delay = 0 (the early stage reads the sample the input stage wrote in the
+    SAME frame, the late stage the one the early stage just fed: no prefetch possible, direct reads across
+    warps); smallest / largest density and diffusion (shortest delay lines the presets allow)."""
+    monkeypatch.setenv("OALSFX_KERNEL", family)
+    lib = _lib()
+    rate = 96000 if variant == "standard-reverb-96k" else 48000
+    rtype = T.reverb if variant == "standard-reverb-96k" else T.eax_reverb
+    if variant == "zero-delays":
+        steps = [ox.default_props(rtype, lib=lib, reflections_delay_=0.0, late_reverb_delay_=0.0), None,
+                 ox.default_props(rtype, lib=lib, reflections_delay_=0.0, late_reverb_delay_=0.0, decay_time_=0.3)]
+    elif variant == "density-extremes":
+        steps = [ox.default_props(rtype, lib=lib, density_=0.0, diffusion_=0.0), None,
+                 ox.default_props(rtype, lib=lib, density_=1.0, diffusion_=1.0, decay_time_=0.1)]
+    else:
+        steps = [None, ox.default_props(rtype, lib=lib, gain_=0.5, late_reverb_gain_=2.0), None]
+    S, blocks = 64, [1024, 700, 1024]
+    chain = [T.equalizer, T.chorus, T.echo, rtype]
+    total = sum(blocks)
+    x = np.stack([H.noise(400 + s, 2, total) for s in range(S)])
+    y = np.empty_like(x)
+    script = [("type", i, t) for i, t in enumerate(chain)] + [("apply",)]
+    with ox.Engine(S, F.stereo, rate, 4, lib=lib) as eng:
+        for i, t in enumerate(chain):
+            eng.set_effect(i, t)
+        at = 0
+        for n, p in zip(blocks, steps):
+            if p is not None:
+                eng.set_effect(3, rtype, p)
+                script += [("props", 3, p), ("apply",)]
+            script += [("mix", n)]
+            y[:, at:at + n] = eng.mix(np.ascontiguousarray(x[:, at:at + n]))
+            at += n
+    for s in (0, 31, 32, 63):
+        expect = H.run_script_orc(checker, F.stereo, rate, 4, script, x[s])
+        _assert_match(expect, y[s], True, f"{family} {variant} stream {s}")
+
+
+@pytest.mark.parametrize("family", ["quartet", "duo"])
+def test_pipelined_kernels_under_load_are_race_free(checker, family, monkeypatch):
+    """16 384 streams (512 tiles: several waves of CTAs, every SM busy) with zero reverb delays, i.e. the
+    configuration in which a stage reads, in the same frame, what the previous stage's warp has just written.
+    Every stream is fed one of four inputs: all copies must agree bit for bit (a lost hand-off ordering would
+    show up as a tile that differs) and equal the checker."""
+    import torch
+    monkeypatch.setenv("OALSFX_KERNEL", family)
+    lib = _lib()
+    S, block, nblocks = 16384, 512, 3
+    chain = [T.equalizer, T.chorus, T.echo, T.eax_reverb]
+    props = ox.default_props(T.eax_reverb, lib=lib, reflections_delay_=0.0, late_reverb_delay_=0.0)
+    base = [H.noise(s, 2, block * nblocks) for s in range(4)]
+    dev = torch.device("cuda:0")
+    outs = []
+    with ox.Engine(S, F.stereo, 48000, 4, lib=lib) as eng:
+        for i, t in enumerate(chain[:3]):
+            eng.set_effect(i, t)
+        eng.set_effect(3, T.eax_reverb, props)
+        for b in range(nblocks):
+            xb = torch.from_numpy(np.stack([v[b * block:(b + 1) * block] for v in base])).to(dev)
+            x = xb.repeat(S // 4, 1, 1).contiguous()
+            y = torch.empty_like(x)
+            eng.mix(x, y, frames=block, stream=torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            outs.append(y)
+    y = torch.cat(outs, dim=1)
+    per = y.view(S // 4, 4, block * nblocks, 2)
+    assert bool((per == per[0:1]).all()), "streams with identical input diverged"
+    script = [("type", i, t) for i, t in enumerate(chain)] + [("props", 3, props), ("apply",)] + [("mix", block)] * nblocks
+    for k in range(4):
+        expect = H.run_script_orc(checker, F.stereo, 48000, 4, script, base[k])
+        _assert_match(expect, per[0, k].cpu().numpy(), True, f"{family} input {k}")
+
+
 @pytest.mark.parametrize("family", ["quartet", "quad", "single"])
 def test_every_kernel_family_on_the_single_reverb_slot(checker, family, monkeypatch):
     """cfg1's signature (one reverb slot, mono): pipeline (default), quad and plain kernels, with a preset
