@@ -270,6 +270,33 @@ def main():
     value = world * S * C * F * args.steps / (total_ms_max * 1e-3)
     assert bool(torch.isfinite(y).all()), "non-finite output"
 
+    # -- the optional all-streams output bus (BASELINE config 4): per-GPU deterministic partial sum of the block
+    #    just mixed + one NCCL all-reduce of the [frames][channels] bus over NVLink.  Reported beside the headline
+    #    number, not inside its timed region (the reference has no such bus).
+    bus = torch.zeros((F, C), device=dev, dtype=torch.float32)
+    bus_steps = max(3, min(args.steps, 10))
+
+    def step_bus():
+        eng.reduce_bus(F, y, bus, stream=stream)
+        if world > 1:
+            dist.all_reduce(bus, op=dist.ReduceOp.SUM)
+
+    step_bus()
+    barrier()
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b0.record()
+    for _ in range(bus_steps):
+        step_bus()
+    b1.record()
+    barrier()
+    t = torch.tensor([b0.elapsed_time(b1) / bus_steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    bus_info = {"ms_per_block": float(t.item()),
+                "what": "oalsfx_engine_reduce_bus (two coalesced passes over the block's output)" +
+                        (f" + NCCL all_reduce of [{F}][{C}] fp32 over {world} GPUs" if world > 1 else ""),
+                "bytes_read_per_gpu": S * F * C * 4}
+
     # -- end to end through the C ABI with host buffers ---------------------------------------------------
     e2e = None
     if not args.skip_e2e:
@@ -320,6 +347,7 @@ def main():
                      "peak_source": peak_src},
         "clocks": clocks.summary(),
         "gpu_launches": launches,
+        "bus": bus_info,
         "device_bytes": eng.device_bytes,
     }
     if e2e is not None:

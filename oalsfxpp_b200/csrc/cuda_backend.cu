@@ -144,6 +144,50 @@ __global__ void __launch_bounds__(256) float_to_s16_kernel(const float* __restri
 	}
 }
 
+// Stream-major buffers are a row-major matrix [stream][frame * C + c]: column sums in two coalesced,
+// deterministic passes.  Pass 1: a CTA sums kBusRows consecutive rows of a 1024-column slab (each thread
+// one float4 column group, rows in ascending order) into partial[row group][column]; pass 2 sums the row
+// groups in ascending order.  Reads the matrix once at full HBM rate (the generic kernel above strides
+// by a whole row between threads and moves 8x the bytes).
+constexpr int kBusRows = 128;
+
+__global__ void __launch_bounds__(256) bus_partial_kernel(const float* __restrict__ data, long long row_stride, int rows, int cols4,
+	float4* __restrict__ partial)
+{
+	const int col4 = blockIdx.x * blockDim.x + threadIdx.x; // float4 column index
+	if (col4 >= cols4) {
+		return;
+	}
+	const int r0 = blockIdx.y * kBusRows;
+	const int r1 = min(r0 + kBusRows, rows);
+	float4 acc = make_float4(0.0F, 0.0F, 0.0F, 0.0F);
+	for (int r = r0; r < r1; ++r) {
+		const float4 v = __ldcs(reinterpret_cast<const float4*>(data + r * row_stride) + col4);
+		acc.x += v.x;
+		acc.y += v.y;
+		acc.z += v.z;
+		acc.w += v.w;
+	}
+	partial[static_cast<long long>(blockIdx.y) * cols4 + col4] = acc;
+}
+
+__global__ void __launch_bounds__(256) bus_final_kernel(const float4* __restrict__ partial, int groups, int cols4, float4* __restrict__ bus)
+{
+	const int col4 = blockIdx.x * blockDim.x + threadIdx.x;
+	if (col4 >= cols4) {
+		return;
+	}
+	float4 acc = make_float4(0.0F, 0.0F, 0.0F, 0.0F);
+	for (int g = 0; g < groups; ++g) {
+		const float4 v = partial[static_cast<long long>(g) * cols4 + col4];
+		acc.x += v.x;
+		acc.y += v.y;
+		acc.z += v.z;
+		acc.w += v.w;
+	}
+	bus[col4] = acc;
+}
+
 class CudaBackend final : public Backend {
 public:
 	explicit CudaBackend(int device) : device_(device) {}
@@ -315,7 +359,30 @@ public:
 		if (!bind()) {
 			return false;
 		}
-		reduce_bus_kernel<<<static_cast<unsigned>(frames * channels), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+		cudaStream_t st = static_cast<cudaStream_t>(stream);
+		const long long cols = static_cast<long long>(frames) * channels;
+		const bool rows_contiguous = cs == 1 && fs == channels && ls == cols && ts == ls * kLanes && cols % 4 == 0 &&
+			((reinterpret_cast<unsigned long long>(data) | reinterpret_cast<unsigned long long>(bus)) & 15ULL) == 0;
+		if (rows_contiguous) {
+			const int groups = (num_streams + kBusRows - 1) / kBusRows;
+			const int cols4 = static_cast<int>(cols / 4);
+			const size_t need = static_cast<size_t>(groups) * static_cast<size_t>(cols) * sizeof(float);
+			if (need > bus_partial_bytes_) {
+				cudaFree(bus_partial_);
+				bus_partial_ = nullptr;
+				bus_partial_bytes_ = 0;
+				if (!check(cudaMalloc(&bus_partial_, need), "cudaMalloc(bus partials)")) {
+					return false;
+				}
+				bus_partial_bytes_ = need;
+			}
+			const unsigned gx = static_cast<unsigned>((cols4 + 255) / 256);
+			bus_partial_kernel<<<dim3(gx, static_cast<unsigned>(groups)), 256, 0, st>>>(data, ls, num_streams, cols4,
+				static_cast<float4*>(bus_partial_));
+			bus_final_kernel<<<gx, 256, 0, st>>>(static_cast<const float4*>(bus_partial_), groups, cols4, reinterpret_cast<float4*>(bus));
+			return check(cudaGetLastError(), "bus_partial_kernel / bus_final_kernel");
+		}
+		reduce_bus_kernel<<<static_cast<unsigned>(frames * channels), 256, 0, st>>>(
 			data, ts, ls, fs, cs, num_streams, channels, bus);
 		return check(cudaGetLastError(), "reduce_bus_kernel");
 	}
@@ -395,6 +462,7 @@ public:
 
 	~CudaBackend() override
 	{
+		cudaFree(bus_partial_);
 		for (cudaEvent_t ev : events_) {
 			if (ev) {
 				cudaEventDestroy(ev);
@@ -411,6 +479,8 @@ private:
 	size_t next_event_ = 0;
 	bool carveout_done_[kKernelEnd] = {};
 	size_t tune_dyn_smem_ = 0;
+	void* bus_partial_ = nullptr;      // row-group partial sums of the bus reduction
+	size_t bus_partial_bytes_ = 0;
 };
 
 } // namespace

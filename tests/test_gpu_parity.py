@@ -352,6 +352,28 @@ def test_tiled_layout_and_bus_reduce():
     assert np.max(np.abs(bus.cpu().numpy() - want)) <= 1e-5 * np.sqrt(S)
 
 
+def test_stream_major_bus_reduce_is_exact_enough_and_deterministic():
+    """The coalesced two-pass reduction (row groups of 128 streams, then the groups): equals the float64 sum
+    of the per-stream outputs within 1e-5 * sqrt(S) and is bit-identical from call to call."""
+    import torch
+    lib = _lib()
+    S, n = 1000, 512  # not a multiple of the row group: the last group is short
+    x = np.stack([H.noise(s, 2, n) for s in range(S)])
+    with ox.Engine(S, F.stereo, 48000, 1, lib=lib) as eng:
+        eng.set_effect(0, T.echo)
+        xd = torch.from_numpy(x).cuda()
+        yd = torch.empty_like(xd)
+        eng.mix(xd, yd, frames=n)
+        a = torch.zeros(n, 2, device="cuda")
+        b = torch.zeros(n, 2, device="cuda")
+        eng.reduce_bus(n, yd, a)
+        eng.reduce_bus(n, yd, b)
+        torch.cuda.synchronize()
+    want = yd.cpu().numpy().astype(np.float64).sum(axis=0)
+    assert np.max(np.abs(a.cpu().numpy() - want)) <= 1e-5 * np.sqrt(S)
+    assert bool((a == b).all())
+
+
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()
