@@ -518,7 +518,9 @@ struct oalsfx_engine {
 			// (twice the warps per tile) wins -- measured on B200, 4-slot stereo chain, ms per 1024-frame block:
 			// 128 tiles 0.47 (quartet) vs 0.63 (duo); 256 tiles 0.64 vs 0.64; 2048 tiles 3.6 vs 3.07.
 			constexpr int kPipelineMaxTiles = 160;
-			const bool few_tiles = a.tile_count <= kPipelineMaxTiles;
+			// (Not for the tile slices of the host-buffer path: there the copies bound the step, and the duo
+			// kernel measured 12.4 ms per step against 13.4 ms with quartet slices.)
+			const bool few_tiles = a.tile_count <= kPipelineMaxTiles && slice_count == 0;
 			if (whole_tiles && (family == 3 || (family == 2 && few_tiles)) && quartet_for_twin(ki.id) >= 0) {
 				id = quartet_for_twin(ki.id);
 			} else if (whole_tiles && family >= 2 && duo_for_twin(ki.id) >= 0) {
@@ -768,7 +770,11 @@ int oalsfx_engine_mix(oalsfx_engine* e, int frames, const float* src, float* dst
 		if (e->groups_dirty && !e->rebuild_groups()) {
 			return e->fail(OALSFX_ERR_DEVICE, "Group table upload failed: " + e->be->error());
 		}
-		const int slices = std::min(e->tiles / 64, 16);
+		int max_slices = 16;
+		if (const char* tune = std::getenv("OALSFX_TUNE_SLICES")) { // experiments only
+			max_slices = std::max(2, std::atoi(tune));
+		}
+		const int slices = std::min(e->tiles / 64, max_slices);
 		if (frames <= kMaxBlockFrames && e->groups.size() == 1 && e->groups[0].identity && slices >= 2 &&
 			layout == OALSFX_LAYOUT_STREAM_MAJOR) {
 			if (!e->pipe_in) {
