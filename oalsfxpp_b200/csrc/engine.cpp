@@ -527,7 +527,9 @@ struct oalsfx_engine {
 				id = duo_for_twin(ki.id);
 			} else if (whole_tiles && family >= 2 && quartet_for_twin(ki.id) >= 0) {
 				id = quartet_for_twin(ki.id); // no duo entry for this signature (single reverb slot)
-			} else if (whole_tiles && family >= 1 && quad_for_twin(ki.id) >= 0) {
+			} else if (whole_tiles && (family == 1 || (family >= 2 && few_tiles)) && quad_for_twin(ki.id) >= 0) {
+				// four lanes per stream: only pays when tiles are scarce (cfg3's chain, B200: 32 tiles 1.08 ms vs 1.19
+				// thread-per-stream; 512 tiles 1.46 vs 1.39; 2048 tiles 4.4 vs 1.8)
 				id = quad_for_twin(ki.id);
 			}
 			return be->launch_mix(id, a, stream);
