@@ -34,9 +34,16 @@ namespace duo {
 #endif
 
 constexpr int kDuoUnroll = OALSFX_DUO_UNROLL;
+#ifndef OALSFX_DUO_UNROLL_FRONT
+#define OALSFX_DUO_UNROLL_FRONT OALSFX_DUO_UNROLL
+#endif
+#ifndef OALSFX_DUO_UNROLL_BACK
+#define OALSFX_DUO_UNROLL_BACK OALSFX_DUO_UNROLL
+#endif
 #ifndef OALSFX_DUO_CHUNK
 #define OALSFX_DUO_CHUNK 4
 #endif
+constexpr int kDuoUnrollFront = OALSFX_DUO_UNROLL_FRONT, kDuoUnrollBack = OALSFX_DUO_UNROLL_BACK;
 constexpr int kDuoChunk = OALSFX_DUO_CHUNK; // frames per hand-off (a multiple of the 4-frame output row batch)
 constexpr int kBarFull = 0;            // named barriers 0,1: buffer b filled by the front warp
 constexpr int kBarEmpty = 2;           // named barriers 2,3: buffer b drained by the back warp
@@ -199,7 +206,7 @@ __global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(
 				xin[3 * kIn][1 % CT][lane] = c1.w;
 			}
 			bar_sync<kBarEmpty>(b);
-#pragma unroll (kDuoUnroll)
+#pragma unroll (kDuoUnrollFront)
 			for (int f = 0; f < count; ++f) {
 				const int i = first + f;
 				float x[CT], acc[CT];
@@ -255,7 +262,7 @@ __global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(
 			const int first = ci * kDuoChunk;
 			const int count = min(kDuoChunk, a.frames - first);
 			bar_sync<kBarFull>(b);
-#pragma unroll (kDuoUnroll)
+#pragma unroll (kDuoUnrollBack)
 			for (int f = 0; f < count; ++f) {
 				const int i = first + f;
 				float x[CT], acc[CT];

@@ -27,8 +27,9 @@
 	X(kChainStereo, 2, false, FxEqualizer, FxModDelay, FxEcho, FxReverb) \
 	/* cfg3: flanger + ring modulator + distortion + compressor, mono */ \
 	X(kChain2Mono, 1, false, FxModDelay, FxRingMod, FxDistortion, FxCompressor) \
-	/* cfg1: one (EAX) reverb slot, mono */ \
+	/* cfg1: one (EAX) reverb slot, mono -- and the same for stereo, the demo program's usual case */ \
 	X(kReverbMono, 1, false, FxReverb, FxNull, FxNull, FxNull) \
+	X(kReverbStereo, 2, false, FxReverb, FxNull, FxNull, FxNull) \
 	/* cfg0: one echo slot, stereo */ \
 	X(kEchoStereo, 2, false, FxEcho, FxNull, FxNull, FxNull)
 
@@ -52,7 +53,8 @@
 #define OALSFX_QUARTET_TABLE(TX) \
 	TX(kQuartetChainStereo, 2, FxEqualizer, FxModDelay, FxEcho, FxReverb, kChainStereo) \
 	/* cfg1: one (EAX) reverb slot, mono: few streams, latency-bound -- more warps per tile is the lever */ \
-	TX(kQuartetReverbMono, 1, FxReverb, FxNull, FxNull, FxNull, kReverbMono)
+	TX(kQuartetReverbMono, 1, FxReverb, FxNull, FxNull, FxNull, kReverbMono) \
+	TX(kQuartetReverbStereo, 2, FxReverb, FxNull, FxNull, FxNull, kReverbStereo)
 
 namespace oalsfx {
 

@@ -264,8 +264,9 @@ def test_pipelined_kernels_under_load_are_race_free(checker, family, monkeypatch
         _assert_match(expect, per[0, k].cpu().numpy(), True, f"{family} input {k}")
 
 
+@pytest.mark.parametrize("fmt", [F.mono, F.stereo])
 @pytest.mark.parametrize("family", ["quartet", "quad", "single"])
-def test_every_kernel_family_on_the_single_reverb_slot(checker, family, monkeypatch):
+def test_every_kernel_family_on_the_single_reverb_slot(checker, family, fmt, monkeypatch):
     """cfg1's signature (one reverb slot, mono): pipeline (default), quad and plain kernels, with a preset
     change mid-stream (tap cross-fade + gain ramp), a modulated preset and odd block sizes."""
     monkeypatch.setenv("OALSFX_KERNEL", family)
@@ -273,12 +274,12 @@ def test_every_kernel_family_on_the_single_reverb_slot(checker, family, monkeypa
     S = 96
     blocks = [1024, 512, 1023, 1024, 6]
     total = sum(blocks)
-    x = np.stack([H.noise(50 + s, 1, total) for s in range(S)])
+    x = np.stack([H.noise(50 + s, ox.channel_count(fmt), total) for s in range(S)])
     y = np.empty_like(x)
     presets = [None, ox.reverb_preset("Default", "forest", lib=lib), None,
                ox.default_props(T.eax_reverb, lib=lib, modulation_depth_=0.8, modulation_time_=0.6), None]
     script = [("type", 0, T.eax_reverb), ("apply",)]
-    with ox.Engine(S, F.mono, 48000, 1, lib=lib) as eng:
+    with ox.Engine(S, fmt, 48000, 1, lib=lib) as eng:
         eng.set_effect(0, T.eax_reverb)
         at = 0
         for n, p in zip(blocks, presets):
@@ -289,7 +290,7 @@ def test_every_kernel_family_on_the_single_reverb_slot(checker, family, monkeypa
             y[:, at:at + n] = eng.mix(np.ascontiguousarray(x[:, at:at + n]))
             at += n
     for s in (0, 31, 32, 95):
-        expect = H.run_script_orc(checker, F.mono, 48000, 1, script, x[s])
+        expect = H.run_script_orc(checker, fmt, 48000, 1, script, x[s])
         _assert_match(expect, y[s], True, f"{family} stream {s}")
 
 
