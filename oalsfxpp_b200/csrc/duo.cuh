@@ -4,14 +4,18 @@
 // ring access of a warp is one full 128-byte line), but the slots are split over two warps so that
 // each keeps only its own recurrent state in registers:
 //
-//   front warp : source encode + dry mix + slots 0..2        (cfg4: equalizer, chorus, echo)
-//   back  warp : slot 3 + output                             (cfg4: EAX reverb, 24-read cp.async window)
+//   front warp : source encode + dry mix + slots 0..2 + the reverb's input stage
+//                                                            (cfg4: equalizer, chorus, echo; B->A + shelves + main-line feed)
+//   back  warp : the rest of slot 3 + output rows            (cfg4: EAX reverb early/late halves, batched 16-byte cp.async window)
 //
 // The front warp hands the input frame and the partially summed bus to the back warp through a
 // double-buffered shared-memory exchange (kDuoChunk frames per hand-off, named barriers), so the
 // bus never touches HBM and the per-sample summation order stays dry, slot 0, 1, 2, 3 -- exactly
-// the reference's (oalsfxpp.cpp:2984-3037).  Per-thread registers drop from ~240 to ~130/~160,
+// the reference's (oalsfxpp.cpp:2984-3037).  Per-thread registers drop from ~240 to 168,
 // which doubles the warps in flight, and the two halves of a stream's work overlap in time.
+// Measured operating point (B200, profiles/r01_history.md): 25 KB of shared memory per CTA, 5 CTAs per SM
+// with the 135 KB carve-out and the remaining ~93 KB as L1 for the stream-major input rows: 3.07 ms per
+// 1024-frame block of 65 536 streams.
 //
 // Host-checked requirements (as for the quad kernels): no send shelf filter active, frames >= 2,
 // every tile of the launch takes part with all of its lanes.
@@ -94,8 +98,8 @@ __global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(
 	const __grid_constant__ MixArgs a)
 {
 	// A reverb in slot 3 is split: its input stage (B->A conversion, shelf filters, main-line feed,
-	// ~150 of its ~830 instructions per sample) runs in the front warp, which balances the two warps.
-	// The front warp runs at most two hand-offs (32 frames) ahead; the main ring keeps 256 spare frames
+	// ~110 instructions per sample) runs in the front warp, which balances the two warps (500 / 413).
+	// The front warp runs at most two hand-offs (8 frames) ahead; the main ring keeps 256 spare frames
 	// beyond its longest tap (oalsfxpp.cpp:6573), so feeding it early cannot overwrite a pending read.
 	constexpr bool back_has_window = std::is_same<F3, FxReverb>::value;
 	constexpr bool split_reverb = back_has_window;
