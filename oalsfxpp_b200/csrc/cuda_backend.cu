@@ -171,21 +171,38 @@ __global__ void __launch_bounds__(256) bus_partial_kernel(const float* __restric
 	partial[static_cast<long long>(blockIdx.y) * cols4 + col4] = acc;
 }
 
+// 32 float4 columns per CTA, 8 slices of the row groups per column; slice sums are combined in slice order
+// (fixed summation order, independent of scheduling).
 __global__ void __launch_bounds__(256) bus_final_kernel(const float4* __restrict__ partial, int groups, int cols4, float4* __restrict__ bus)
 {
-	const int col4 = blockIdx.x * blockDim.x + threadIdx.x;
-	if (col4 >= cols4) {
-		return;
-	}
+	__shared__ float4 part[8][32];
+	const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+	const int col4 = blockIdx.x * 32 + lane;
 	float4 acc = make_float4(0.0F, 0.0F, 0.0F, 0.0F);
-	for (int g = 0; g < groups; ++g) {
-		const float4 v = partial[static_cast<long long>(g) * cols4 + col4];
-		acc.x += v.x;
-		acc.y += v.y;
-		acc.z += v.z;
-		acc.w += v.w;
+	if (col4 < cols4) {
+		const int g0 = static_cast<int>(static_cast<long long>(groups) * slice / 8);
+		const int g1 = static_cast<int>(static_cast<long long>(groups) * (slice + 1) / 8);
+		for (int g = g0; g < g1; ++g) {
+			const float4 v = partial[static_cast<long long>(g) * cols4 + col4];
+			acc.x += v.x;
+			acc.y += v.y;
+			acc.z += v.z;
+			acc.w += v.w;
+		}
 	}
-	bus[col4] = acc;
+	part[slice][lane] = acc;
+	__syncthreads();
+	if (slice == 0 && col4 < cols4) {
+#pragma unroll
+		for (int k = 1; k < 8; ++k) {
+			const float4 v = part[k][lane];
+			acc.x += v.x;
+			acc.y += v.y;
+			acc.z += v.z;
+			acc.w += v.w;
+		}
+		bus[col4] = acc;
+	}
 }
 
 class CudaBackend final : public Backend {
@@ -379,7 +396,8 @@ public:
 			const unsigned gx = static_cast<unsigned>((cols4 + 255) / 256);
 			bus_partial_kernel<<<dim3(gx, static_cast<unsigned>(groups)), 256, 0, st>>>(data, ls, num_streams, cols4,
 				static_cast<float4*>(bus_partial_));
-			bus_final_kernel<<<gx, 256, 0, st>>>(static_cast<const float4*>(bus_partial_), groups, cols4, reinterpret_cast<float4*>(bus));
+			bus_final_kernel<<<static_cast<unsigned>((cols4 + 31) / 32), 256, 0, st>>>(static_cast<const float4*>(bus_partial_), groups, cols4,
+				reinterpret_cast<float4*>(bus));
 			return check(cudaGetLastError(), "bus_partial_kernel / bus_final_kernel");
 		}
 		reduce_bus_kernel<<<static_cast<unsigned>(frames * channels), 256, 0, st>>>(
