@@ -486,7 +486,12 @@ struct FxReverbT {
 			pf_cur = pf_col + row * (kTaps * kLanes);
 			body<CT, true>(c, wet, acc, channels, pos); // branch-free: every read is a shared-memory load
 		} else {
-			primed = false;
+			if (primed) {
+				// leaving the batched mode: nothing of the window may still be in flight when it is primed
+				// again (an old copy landing after a new one would put stale rows into the window)
+				cp_async_wait_group<0>();
+				primed = false;
+			}
 			body<CT, false>(c, wet, acc, channels, pos);
 		}
 #else
