@@ -338,6 +338,10 @@ public:
 			quartet::quartet_kernel<CT, F0, F1, F2, F3><<<static_cast<unsigned>(args.tile_count), quartet::kThreads, tune_dyn_smem_, st>>>(args); break;
 			OALSFX_QUARTET_TABLE(OALSFX_TX)
 #undef OALSFX_TX
+#define OALSFX_TBX(id, Fx, kind) \
+		case id: mix_kernel<0, true, Fx, FxNull, FxNull, FxNull, true><<<blocks, threads, 0, st>>>(args); break;
+			OALSFX_TABMODE_TABLE(OALSFX_TBX)
+#undef OALSFX_TBX
 		default:
 			error_ = "unknown kernel id";
 			return false;

@@ -63,6 +63,7 @@ struct Group {
 	GroupKey key;
 	bool identity = false;     // covers tiles 0..T-1 with all lanes
 	bool full_tiles = false;   // every listed tile takes part with all of its (existing) lanes
+	bool table = false;        // table mode: key.fx[] holds effect KINDS, streams differ in parameters
 	size_t tile_begin = 0;     // into the concatenated tile list
 	int tile_count = 0;
 };
@@ -97,6 +98,15 @@ struct oalsfx_engine {
 	size_t stage_cap = 0;                // floats
 	long long device_bytes = 0;
 
+	// Table mode (many parameter sets per engine): coefficient blocks of every class and every stream's
+	// class indices in HBM, read by the kTab* kernels.  Rebuilt with the groups.
+	SlotCoef* slot_table_dev = nullptr;
+	size_t slot_table_cap = 0;
+	SendCoef* send_table_dev = nullptr;
+	size_t send_table_cap = 0;
+	int32_t* lane_class_dev[kMaxSlots] = {};
+	int32_t* lane_send_dev = nullptr;
+
 	std::vector<Group> groups;
 	bool groups_dirty = true;
 	long long launches = 0;
@@ -126,6 +136,12 @@ struct oalsfx_engine {
 		}
 		be->release(send_state);
 		be->release(tile_list);
+		be->release(slot_table_dev);
+		be->release(send_table_dev);
+		be->release(lane_send_dev);
+		for (int s = 0; s < kMaxSlots; ++s) {
+			be->release(lane_class_dev[s]);
+		}
 		be->release(stage_in);
 		be->release(stage_out);
 		be->stream_destroy(pipe_in);
@@ -338,6 +354,72 @@ struct oalsfx_engine {
 		return k;
 	}
 
+	template <class T>
+	bool grow(T*& p, size_t& cap, size_t need)
+	{
+		if (need <= cap) {
+			return true;
+		}
+		be->sync(nullptr);
+		if (p) {
+			device_bytes -= static_cast<long long>(cap * sizeof(T));
+			be->release(p);
+		}
+		cap = need * 2;
+		p = static_cast<T*>(dev_alloc(cap * sizeof(T)));
+		return p != nullptr;
+	}
+
+	// Table mode: every class's coefficient block, every send class's five send blocks and every stream's
+	// class indices go to HBM (~0.7 KB per class, 20 bytes per stream).
+	bool upload_tables()
+	{
+		std::vector<SlotCoef> coefs(classes.size());
+		for (size_t i = 0; i < classes.size(); ++i) {
+			coefs[i] = classes[i].coef;
+		}
+		std::vector<SendCoef> sends(send_classes.size() * kSendCount);
+		for (size_t i = 0; i < send_classes.size(); ++i) {
+			sends[i * kSendCount] = send_classes[i].direct_coef;
+			for (int k = 0; k < kMaxSlots; ++k) {
+				sends[i * kSendCount + 1 + static_cast<size_t>(k)] = send_classes[i].aux_coef[k];
+			}
+		}
+		const size_t padded = static_cast<size_t>(tiles) * kLanes;
+		size_t lane_cap = lane_send_dev ? padded : 0;
+		if (!grow(slot_table_dev, slot_table_cap, coefs.size()) || !grow(send_table_dev, send_table_cap, sends.size())) {
+			return false;
+		}
+		if (!lane_send_dev) {
+			lane_send_dev = static_cast<int32_t*>(dev_alloc(padded * sizeof(int32_t)));
+			for (int s = 0; s < kMaxSlots; ++s) {
+				lane_class_dev[s] = static_cast<int32_t*>(dev_alloc(padded * sizeof(int32_t)));
+				if (!lane_class_dev[s]) {
+					return false;
+				}
+			}
+			if (!lane_send_dev) {
+				return false;
+			}
+		}
+		(void)lane_cap;
+		bool ok = be->upload(slot_table_dev, coefs.data(), coefs.size() * sizeof(SlotCoef), nullptr) &&
+			be->upload(send_table_dev, sends.data(), sends.size() * sizeof(SendCoef), nullptr);
+		std::vector<int32_t> idx(padded, 0);
+		for (int s = 0; s < streams; ++s) {
+			idx[static_cast<size_t>(s)] = send_class[static_cast<size_t>(s)];
+		}
+		ok = ok && be->upload(lane_send_dev, idx.data(), padded * sizeof(int32_t), nullptr) && be->sync(nullptr);
+		for (int k = 0; k < kMaxSlots && ok; ++k) {
+			std::fill(idx.begin(), idx.end(), 0);
+			for (int s = 0; s < streams; ++s) {
+				idx[static_cast<size_t>(s)] = fx_class[k][static_cast<size_t>(s)];
+			}
+			ok = be->upload(lane_class_dev[k], idx.data(), padded * sizeof(int32_t), nullptr) && be->sync(nullptr);
+		}
+		return ok;
+	}
+
 	bool rebuild_groups()
 	{
 		if (classes.size() > 256) {
@@ -367,10 +449,36 @@ struct oalsfx_engine {
 			}
 			v.back().mask |= 1U << (s % kLanes);
 		}
+		// One launch per parameter class is fine for a handful of classes (each runs the fused kernels with
+		// constant-bank coefficients).  Beyond that the launches multiply -- every class touches most tiles --
+		// so the streams are grouped by effect KINDS only and the kTab* kernels fetch each stream's own
+		// coefficient block from HBM.
+		constexpr size_t kTableModeMinGroups = 8;
+		const bool table_mode = by_key.size() > kTableModeMinGroups;
+		if (table_mode) {
+			by_key.clear();
+			for (int s = 0; s < streams; ++s) {
+				GroupKey k = key_of(s);
+				for (int i = 0; i < kMaxSlots; ++i) {
+					k.fx[i] = kind_of_type(classes[static_cast<size_t>(k.fx[i])].type);
+				}
+				k.send = 0;
+				std::vector<TileRef>& v = by_key[k];
+				const uint32_t tile = static_cast<uint32_t>(s / kLanes);
+				if (v.empty() || v.back().tile != tile) {
+					v.push_back(TileRef{tile, 0});
+				}
+				v.back().mask |= 1U << (s % kLanes);
+			}
+			if (!upload_tables()) {
+				return false;
+			}
+		}
 		std::vector<TileRef> all;
 		for (auto& kv : by_key) {
 			Group g;
 			g.key = kv.first;
+			g.table = table_mode;
 			g.tile_begin = all.size();
 			g.tile_count = static_cast<int>(kv.second.size());
 			g.full_tiles = true;
@@ -426,16 +534,26 @@ struct oalsfx_engine {
 			a.tile_count = slice_count;
 		}
 		a.send_state = send_state;
+		if (g.table) {
+			a.slot_table = slot_table_dev;
+			a.send_table = send_table_dev;
+			a.lane_send = lane_send_dev;
+			return;
+		}
 		const SendClass& sc = send_classes[static_cast<size_t>(g.key.send)];
 		a.direct = sc.direct_coef;
 	}
 
 	void fill_slot(MixArgs& a, const Group& g, int pos, int slot, bool first_block) const
 	{
-		const FxClass& fc = classes[static_cast<size_t>(g.key.fx[slot])];
-		const SendClass& sc = send_classes[static_cast<size_t>(g.key.send)];
-		a.slot[pos] = fc.coef;
-		a.aux[pos] = sc.aux_coef[slot];
+		if (g.table) {
+			a.lane_class[pos] = lane_class_dev[slot];
+		} else {
+			const FxClass& fc = classes[static_cast<size_t>(g.key.fx[slot])];
+			const SendClass& sc = send_classes[static_cast<size_t>(g.key.send)];
+			a.slot[pos] = fc.coef;
+			a.aux[pos] = sc.aux_coef[slot];
+		}
 		a.aux_index[pos] = slot;
 		a.ring[pos] = ring[slot];
 		a.ring_tile_stride[pos] = static_cast<long long>(ring_cap[slot]) * kLanes;
@@ -478,6 +596,34 @@ struct oalsfx_engine {
 	bool launch_group(const Group& g, int frames, const float* src, float* dst, int layout,
 		long long frames_total, long long frame0, bool first_block, void* stream)
 	{
+		if (g.table) {
+			// key.fx[] holds the kinds; one exact single-effect pass per slot, coefficients from the tables
+			bool first = true;
+			for (int s = 0; s < kMaxSlots; ++s) {
+				if (g.key.fx[s] == kKindNull) {
+					continue;
+				}
+				MixArgs a;
+				fill_common(a, g, frames, src, dst, layout, frames_total, frame0);
+				a.with_dry = first ? 1 : 0;
+				a.accumulate = first ? 0 : 1;
+				fill_slot(a, g, 0, s, first_block);
+				++launches;
+				if (!be->launch_mix(tab_kernel_for_kind(g.key.fx[s]), a, stream)) {
+					return false;
+				}
+				first = false;
+			}
+			if (first) {
+				MixArgs a;
+				fill_common(a, g, frames, src, dst, layout, frames_total, frame0);
+				a.with_dry = 1;
+				fill_slot(a, g, 0, 0, first_block);
+				++launches;
+				return be->launch_mix(kTabDry, a, stream);
+			}
+			return true;
+		}
 		const SendClass& sc = send_classes[static_cast<size_t>(g.key.send)];
 		int kinds[kMaxSlots];
 		bool any_filter = sc.direct_coef.filter_type != 0;

@@ -56,6 +56,19 @@
 	TX(kQuartetReverbMono, 1, FxReverb, FxNull, FxNull, FxNull, kReverbMono) \
 	TX(kQuartetReverbStereo, 2, FxReverb, FxNull, FxNull, FxNull, kReverbStereo)
 
+// Table-mode kernels (mix.cuh, TABLE = true): the single-effect "Gen" passes with per-stream coefficient blocks
+// read from HBM, for engines whose streams carry many different parameter sets.  TBX(id, Fx, kind).
+#define OALSFX_TABMODE_TABLE(TBX) \
+	TBX(kTabDry, FxNull, kKindNull) \
+	TBX(kTabModDelay, FxModDelay, kKindModDelay) \
+	TBX(kTabCompressor, FxCompressor, kKindCompressor) \
+	TBX(kTabDedicated, FxDedicated, kKindDedicated) \
+	TBX(kTabDistortion, FxDistortion, kKindDistortion) \
+	TBX(kTabEcho, FxEcho, kKindEcho) \
+	TBX(kTabEqualizer, FxEqualizer, kKindEqualizer) \
+	TBX(kTabRingMod, FxRingMod, kKindRingMod) \
+	TBX(kTabReverb, FxReverb, kKindReverb)
+
 namespace oalsfx {
 
 enum KernelId : int {
@@ -73,6 +86,9 @@ enum KernelId : int {
 #define OALSFX_TX(id, CT, F0, F1, F2, F3, twin) id,
 	OALSFX_QUARTET_TABLE(OALSFX_TX)
 #undef OALSFX_TX
+#define OALSFX_TBX(id, Fx, kind) id,
+	OALSFX_TABMODE_TABLE(OALSFX_TBX)
+#undef OALSFX_TBX
 	kKernelEnd
 };
 
@@ -122,6 +138,15 @@ inline const char* kernel_name(int id);
 // Effect "kind" = which processor handles an FxType (chorus/flanger and reverb/EAX share one).
 enum FxKind : int { kKindNull, kKindModDelay, kKindCompressor, kKindDedicated, kKindDistortion, kKindEcho,
 	kKindEqualizer, kKindRingMod, kKindReverb };
+
+// table-mode kernel id for an effect kind
+inline int tab_kernel_for_kind(int kind)
+{
+#define OALSFX_TBX(id, Fx, k) if (kind == k) return id;
+	OALSFX_TABMODE_TABLE(OALSFX_TBX)
+#undef OALSFX_TBX
+	return -1;
+}
 
 template <class F> struct KindOf;
 template <> struct KindOf<FxNull> { static constexpr int value = kKindNull; };
@@ -176,6 +201,9 @@ inline const char* kernel_name(int id)
 #define OALSFX_TX(tid, CT, F0, F1, F2, F3, twin) if (id == tid) return #tid;
 	OALSFX_QUARTET_TABLE(OALSFX_TX)
 #undef OALSFX_TX
+#define OALSFX_TBX(tid, Fx, kind) if (id == tid) return #tid;
+	OALSFX_TABMODE_TABLE(OALSFX_TBX)
+#undef OALSFX_TBX
 	return "?";
 }
 

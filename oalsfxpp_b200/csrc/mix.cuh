@@ -50,6 +50,14 @@ struct MixArgs {
 	SendCoef direct;
 	SendCoef aux[kMaxSlots];
 	SlotCoef slot[kMaxSlots];
+	// Table mode (kTab* kernels): streams of one launch have DIFFERENT parameter sets.  The coefficient
+	// blocks then live in HBM, one per parameter class, and every stream carries the index of its own:
+	//   slot_table[lane_class[p][stream]]                      instead of slot[p]
+	//   send_table[lane_send[stream] * kSendCount + 0 / 1 + i] instead of direct / aux[.] of engine slot i
+	const SlotCoef* slot_table;
+	const int32_t* lane_class[kMaxSlots];
+	const SendCoef* send_table;
+	const int32_t* lane_send;
 };
 
 // Send shelf filters (reference: apply_filters, oalsfxpp.cpp:3101-3143).  Pass-through still
@@ -89,10 +97,17 @@ OALSFX_HD float send_filter_step(const SendCoef& sc, SendHist& h, float x)
 
 // One slot position: encode the source into the slot's 4-channel wet bus (MixHelpers::mix with
 // static gains, oalsfxpp.cpp:2952-2980) and run the effect on it.
-template <int CT, bool SF, class Fx>
+// TABLE: the coefficient blocks come from the per-stream tables in HBM (MixArgs::slot_table ...) instead of
+// the kernel arguments; everything else is identical.
+template <int CT, bool SF, class Fx, bool TABLE = false>
 struct SlotRunner {
 	Fx fx;
 	SendHist hist[SF ? kMaxChannels : 1];
+	const SlotCoef* tab_slot = nullptr;
+	const SendCoef* tab_send = nullptr;
+
+	OALSFX_HD const SlotCoef& coef(const MixArgs& a, int p) const { return TABLE ? *tab_slot : a.slot[p]; }
+	OALSFX_HD const SendCoef& send(const MixArgs& a, int p) const { return TABLE ? *tab_send : a.aux[p]; }
 
 	OALSFX_HD void begin(const MixArgs& a, int p, int tile, int lane, float* prefetch_column)
 	{
@@ -100,9 +115,14 @@ struct SlotRunner {
 			return;
 		}
 		fx.set_prefetch(prefetch_column);
+		if (TABLE) {
+			const long long stream = static_cast<long long>(tile) * kLanes + lane;
+			tab_slot = a.slot_table + a.lane_class[p][stream];
+			tab_send = a.send_table + static_cast<long long>(a.lane_send[stream]) * kSendCount + 1 + a.aux_index[p];
+		}
 		uint32_t* st = a.slot_state[p] + (static_cast<long long>(tile) * kSlotStateWords) * kLanes + lane;
 		float* ring = a.ring[p] ? a.ring[p] + static_cast<long long>(tile) * a.ring_tile_stride[p] + lane : nullptr;
-		fx.template begin<CT>(a.slot[p], st, ring, (a.update_mask >> p) & 1U, a.frames, a.channels);
+		fx.template begin<CT>(coef(a, p), st, ring, (a.update_mask >> p) & 1U, a.frames, a.channels);
 		if (SF) {
 			const uint32_t* ss = a.send_state + (static_cast<long long>(tile) * kSendStateWords +
 				(1 + a.aux_index[p]) * kMaxChannels * 8) * kLanes + lane;
@@ -117,7 +137,7 @@ struct SlotRunner {
 		if (Fx::kIsNull) {
 			return;
 		}
-		const SendCoef& sc = a.aux[p];
+		const SendCoef& sc = send(a, p);
 		float wet[kWetChannels] = {0.0F, 0.0F, 0.0F, 0.0F};
 		if (CT == 2 && !SF) {
 			// wet[k] = (0 + x0 * g[0][k]) + x1 * g[1][k], wet channels (0,1) and (2,3) as pairs
@@ -128,7 +148,7 @@ struct SlotRunner {
 			wet[1] = f2_hi(wa);
 			wet[2] = f2_lo(wb);
 			wet[3] = f2_hi(wb);
-			fx.template step<CT, true>(a.slot[p], wet, acc, a.channels);
+			fx.template step<CT, true>(coef(a, p), wet, acc, a.channels);
 		} else {
 			OALSFX_UNROLL
 			for (int c = 0; c < (CT ? CT : kMaxChannels); ++c) {
@@ -142,7 +162,7 @@ struct SlotRunner {
 					}
 				}
 			}
-			fx.template step<CT, !SF>(a.slot[p], wet, acc, a.channels);
+			fx.template step<CT, !SF>(coef(a, p), wet, acc, a.channels);
 		}
 	}
 
@@ -153,7 +173,7 @@ struct SlotRunner {
 			return;
 		}
 		uint32_t* st = a.slot_state[p] + (static_cast<long long>(tile) * kSlotStateWords) * kLanes + lane;
-		fx.template end_ct<CT>(a.slot[p], st, a.channels);
+		fx.template end_ct<CT>(coef(a, p), st, a.channels);
 	}
 
 	OALSFX_HD void end(const MixArgs& a, int p, int tile, int lane, const float* last1, const float* last2)
@@ -162,7 +182,7 @@ struct SlotRunner {
 			return;
 		}
 		uint32_t* st = a.slot_state[p] + (static_cast<long long>(tile) * kSlotStateWords) * kLanes + lane;
-		fx.template end_ct<CT>(a.slot[p], st, a.channels);
+		fx.template end_ct<CT>(coef(a, p), st, a.channels);
 		uint32_t* ss = a.send_state + (static_cast<long long>(tile) * kSendStateWords +
 			(1 + a.aux_index[p]) * kMaxChannels * 8) * kLanes + lane;
 		for (int c = 0; c < a.channels; ++c) {
@@ -190,7 +210,7 @@ struct PrefetchUser {
 
 // `prefetch_column`: this thread's column of its warp's shared-memory prefetch window (kPfWarpFloats
 // floats per warp), or null (CPU test build, kernels without a window) to read the rings directly.
-template <int CT, bool SF, class F0, class F1, class F2, class F3>
+template <int CT, bool SF, class F0, class F1, class F2, class F3, bool TABLE = false>
 OALSFX_HD void mix_stream(const MixArgs& a, int tile, int lane, float* prefetch_column = nullptr)
 {
 	constexpr int pf_user = PrefetchUser<F0, F1, F2, F3>::value;
@@ -198,10 +218,11 @@ OALSFX_HD void mix_stream(const MixArgs& a, int tile, int lane, float* prefetch_
 	const float* src = a.src + tile * a.io_ts + lane * a.io_ls;
 	float* dst = a.dst + tile * a.io_ts + lane * a.io_ls;
 
-	SlotRunner<CT, SF, F0> r0;
-	SlotRunner<CT, SF, F1> r1;
-	SlotRunner<CT, SF, F2> r2;
-	SlotRunner<CT, SF, F3> r3;
+	SlotRunner<CT, SF, F0, TABLE> r0;
+	SlotRunner<CT, SF, F1, TABLE> r1;
+	SlotRunner<CT, SF, F2, TABLE> r2;
+	SlotRunner<CT, SF, F3, TABLE> r3;
+	const SendCoef& direct = TABLE ? a.send_table[static_cast<long long>(a.lane_send[static_cast<long long>(tile) * kLanes + lane]) * kSendCount] : a.direct;
 	r0.begin(a, 0, tile, lane, pf_user == 0 ? prefetch_column : nullptr);
 	r1.begin(a, 1, tile, lane, pf_user == 1 ? prefetch_column : nullptr);
 	r2.begin(a, 2, tile, lane, pf_user == 2 ? prefetch_column : nullptr);
@@ -238,11 +259,11 @@ OALSFX_HD void mix_stream(const MixArgs& a, int tile, int lane, float* prefetch_
 			OALSFX_UNROLL
 			for (int c = 0; c < (CT ? CT : kMaxChannels); ++c) {
 				if (CT || c < channels) {
-					const float v = SF ? send_filter_step(a.direct, dhist[SF ? c : 0], x[c]) : x[c];
+					const float v = SF ? send_filter_step(direct, dhist[SF ? c : 0], x[c]) : x[c];
 					OALSFX_UNROLL
 					for (int k = 0; k < (CT ? CT : kMaxChannels); ++k) {
-						if ((CT || k < channels) && (!SF || audible(a.direct.gains[c][k]))) {
-							acc[k] += v * a.direct.gains[c][k];
+						if ((CT || k < channels) && (!SF || audible(direct.gains[c][k]))) {
+							acc[k] += v * direct.gains[c][k];
 						}
 					}
 				}
@@ -279,10 +300,11 @@ OALSFX_HD void mix_stream(const MixArgs& a, int tile, int lane, float* prefetch_
 }
 
 #if defined(__CUDACC__)
-template <int CT, bool SF, class F0, class F1, class F2, class F3>
+template <int CT, bool SF, class F0, class F1, class F2, class F3, bool TABLE = false>
 __global__ void __launch_bounds__(64) mix_kernel(const __grid_constant__ MixArgs a)
 {
-	constexpr bool has_window = PrefetchUser<F0, F1, F2, F3>::value >= 0;
+	// Table mode: taps differ from lane to lane, so the reverb's warp-wide batched prefetch is off.
+	constexpr bool has_window = !TABLE && PrefetchUser<F0, F1, F2, F3>::value >= 0;
 	__shared__ __align__(16) float window[has_window ? (64 / kLanes) * kPfWarpFloats : 1];
 	const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / kLanes;
 	const int lane = threadIdx.x % kLanes;
@@ -301,7 +323,7 @@ __global__ void __launch_bounds__(64) mix_kernel(const __grid_constant__ MixArgs
 	}
 	// The reverb's batched prefetch is a whole-warp operation: only complete tiles get a window.
 	const bool whole_tile = mask == 0xFFFFFFFFU && (tile + 1) * kLanes <= a.num_streams;
-	mix_stream<CT, SF, F0, F1, F2, F3>(a, tile, lane,
+	mix_stream<CT, SF, F0, F1, F2, F3, TABLE>(a, tile, lane,
 		has_window && whole_tile ? window + (threadIdx.x / kLanes) * kPfWarpFloats + lane : nullptr);
 }
 #endif

@@ -49,7 +49,7 @@ public:
 	}
 	bool launch_mix(int kernel_id, const MixArgs& a, void*) override
 	{
-		if (kernel_id >= kKernelCount) { // a quad kernel: the CPU build runs its thread-per-stream twin
+		if (kernel_id >= kKernelCount && kernel_id < kTabDry) { // a quad / duo / quartet kernel: the CPU build runs its thread-per-stream twin
 			kernel_id = twin_of_quad(kernel_id);
 		}
 		for (int w = 0; w < a.tile_count; ++w) {
@@ -68,6 +68,10 @@ public:
 				case id: mix_stream<CT, SF, F0, F1, F2, F3>(a, tile, lane); break;
 					OALSFX_KERNEL_TABLE(OALSFX_X)
 #undef OALSFX_X
+#define OALSFX_TBX(id, Fx, kind) \
+				case id: mix_stream<0, true, Fx, FxNull, FxNull, FxNull, true>(a, tile, lane); break;
+					OALSFX_TABMODE_TABLE(OALSFX_TBX)
+#undef OALSFX_TBX
 				default:
 					error_ = "unknown kernel id";
 					return false;

@@ -227,3 +227,61 @@ def blocks_of(total, block):
 
 def max_abs_diff(a, b):
     return float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64)))) if a.size else 0.0
+
+
+# ---- shared scenario: every stream its own parameter set (engine table mode) ---------------------------
+def many_parameter_sets(lib, checker, S, frames, block, sample, exact_all):
+    """Every stream its own parameter set (table mode: > 8 distinct classes, coefficient blocks in HBM), two
+    different slot signatures, send filters on some streams, a parameter change in the middle."""
+    import oalsfxpp_b200 as ox
+    from oalsfxpp_b200 import ChannelFormat as F, EffectType as T
+    default = lambda t, **kw: ox.default_props(t, lib=lib, **kw)
+    blocks = blocks_of(frames, block)
+    x = np.stack([noise(500 + s, 2, frames) for s in range(S)])
+
+    def config(s, phase):
+        if s % 5 == 4:  # a different signature in the same engine
+            return [(T.flanger, default(T.flanger, rate_=0.1 + 0.01 * s)), (T.ring_modulator, default(T.ring_modulator, frequency_=300.0 + 7 * s)),
+                    (T.distortion, default(T.distortion, edge_=0.1 + 0.005 * (s % 100))), (T.compressor, None)]
+        return [(T.equalizer, default(T.equalizer, mid1_gain_=0.5 + 0.01 * s + 0.2 * phase)), (T.chorus, default(T.chorus, depth_=0.05 + 0.001 * s)),
+                (T.echo, default(T.echo, delay_=0.02 + 0.001 * s, feedback_=0.3)),
+                (T.eax_reverb if s % 2 else T.reverb, default(T.eax_reverb if s % 2 else T.reverb, gain_=0.1 + 0.002 * s,
+                                                               decay_time_=0.5 + 0.01 * s + 0.3 * phase, reflections_delay_=0.001 * (s % 20)))]
+
+    y = np.empty_like(x)
+    with ox.Engine(S, F.stereo, 48000, 4, lib=lib) as eng:
+        for s in range(S):
+            for slot, (t, p) in enumerate(config(s, 0)):
+                eng.set_effect(slot, t, p, first_stream=s, n_streams=1)
+            if s % 7 == 0:
+                eng.set_sends(direct=(0.8, 0.5, 1.0), aux=[(1.0, 0.25, 1.0)] * 4, first_stream=s, n_streams=1)
+        pos = 0
+        for b, n in enumerate(blocks):
+            if b == 1:
+                for s in range(S):
+                    for slot, (t, p) in enumerate(config(s, 1)):
+                        eng.set_effect(slot, t, p, first_stream=s, n_streams=1)
+            y[:, pos:pos + n] = eng.mix(np.ascontiguousarray(x[:, pos:pos + n]))
+            pos += n
+        launches = eng.launch_count
+    for s in sample:
+        script = []
+        for slot, (t, p) in enumerate(config(s, 0)):
+            script += [("type", slot, t)] + ([("props", slot, p)] if p is not None else [])
+        if s % 7 == 0:
+            script += [("send", -1, (0.8, 0.5, 1.0))] + [("send", i, (1.0, 0.25, 1.0)) for i in range(4)]
+        script += [("apply",)]
+        for b, n in enumerate(blocks):
+            if b == 1:
+                for slot, (t, p) in enumerate(config(s, 1)):
+                    script += [("type", slot, t)] + ([("props", slot, p)] if p is not None else [])
+                script += [("apply",)]
+            script += [("mix", n)]
+        expect = run_script_orc(checker, F.stereo, 48000, 4, script, x[s])
+        exact = s % 5 != 4  # the ring modulator's carrier is the device sinf on the GPU
+        if exact or exact_all:
+            assert np.array_equal(expect, y[s], equal_nan=True), (s, max_abs_diff(expect, y[s]))
+        else:
+            assert max_abs_diff(expect, y[s]) <= 1e-5, s
+    return launches, len(blocks)
+

@@ -157,3 +157,9 @@ def test_host_buffer_mix_is_sliced_without_changing_results(checker):
     for s in (0, 1, 6, 2047, 2048, 4095, 4096, 4099):
         expect = H.run_script_orc(checker, F.stereo, 48000, 2, script, x[s])
         assert np.array_equal(expect, y[s]), s
+
+
+def test_many_parameter_sets_table_mode(checker):
+    launches, nblocks = H.many_parameter_sets(H.emu_lib(), checker, 70, 1500, 512, range(70), exact_all=True)
+    # two kind signatures -> two groups of (dry+slot, 3 accumulate passes): not one launch per parameter set
+    assert launches <= nblocks * 2 * 4

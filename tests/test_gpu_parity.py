@@ -353,6 +353,15 @@ def test_tiled_layout_and_bus_reduce():
     assert np.max(np.abs(bus.cpu().numpy() - want)) <= 1e-5 * np.sqrt(S)
 
 
+def test_many_parameter_sets_table_mode(checker):
+    """1000 streams, every one with its own parameters (table mode: coefficient blocks per stream from HBM),
+    two slot signatures, send filters, a parameter change mid-stream.  A handful of launches per block, not
+    one per parameter set; sampled streams equal the checker."""
+    launches, nblocks = H.many_parameter_sets(_lib(), checker, 1000, 1500, 512, (0, 1, 4, 7, 31, 32, 333, 504, 998, 999),
+                                              exact_all=False)
+    assert launches <= nblocks * 2 * 4
+
+
 def test_stream_major_bus_reduce_is_exact_enough_and_deterministic():
     """The coalesced two-pass reduction (row groups of 128 streams, then the groups): equals the float64 sum
     of the per-stream outputs within 1e-5 * sqrt(S) and is bit-identical from call to call."""
