@@ -37,6 +37,9 @@ public:
 	virtual bool zero_lanes(uint32_t* base, long long tile_stride, int words, const TileRef* tiles, int n_tiles,
 		void* stream) = 0;
 	virtual bool launch_mix(int kernel_id, const MixArgs& args, void* stream) = 0;
+	// The relay kernels (relay.cuh) are device-only code: the CPU test backend answers false and the engine
+	// keeps such groups on the single-effect passes.
+	virtual bool has_relay() const { return false; }
 	// bus[frame*C + c] = sum over streams (fixed order: lane-major tree per tile, then tiles).
 	virtual bool reduce_bus(const float* data, long long ts, long long ls, long long fs, long long cs,
 		int num_streams, int frames, int channels, float* bus, void* stream) = 0;

@@ -15,6 +15,7 @@
 #include "quad.cuh"
 #include "duo.cuh"
 #include "quartet.cuh"
+#include "relay.cuh"
 
 namespace oalsfx {
 namespace {
@@ -342,6 +343,13 @@ public:
 		case id: mix_kernel<0, true, Fx, FxNull, FxNull, FxNull, true><<<blocks, threads, 0, st>>>(args); break;
 			OALSFX_TABMODE_TABLE(OALSFX_TBX)
 #undef OALSFX_TBX
+#define OALSFX_RX(id, CT, HEAVY) \
+		case id: \
+			relay_attributes(id, relay::relay_kernel<CT, HEAVY>); \
+			relay::relay_kernel<CT, HEAVY><<<static_cast<unsigned>(args.tile_count), relay::kThreads, \
+				static_cast<size_t>(args.relay_smem_floats) * sizeof(float), st>>>(args); break;
+			OALSFX_RELAY_TABLE(OALSFX_RX)
+#undef OALSFX_RX
 		default:
 			error_ = "unknown kernel id";
 			return false;
@@ -354,6 +362,18 @@ public:
 	// consecutive frames from L1.  Measured on B200 (gpurun_out/exp13, exp21; 65 536 streams): the optimum
 	// is 4 CTAs per SM with the rest of the 228 KB as L1 (carve-out 46-54 %: 3.07 ms); 5 CTAs (62-80 %) 3.23 ms;
 	// 6 CTAs / ~28 KB of L1 (100 %) 3.8 ms; 3 CTAs 3.2 ms.
+	bool has_relay() const override { return true; }
+
+	// Relay kernels: up to four reverb windows of dynamic shared memory (96 KB), carve-out as large as needed.
+	template <class K> void relay_attributes(int id, K kernel)
+	{
+		if (!carveout_done_[id]) {
+			cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSlots * kPfWarpFloats * static_cast<int>(sizeof(float)));
+			cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+			carveout_done_[id] = true;
+		}
+	}
+
 	template <class K> void prefer_shared(int id, K kernel, int default_carveout)
 	{
 		if (!carveout_done_[id]) {

@@ -113,7 +113,8 @@ struct oalsfx_engine {
 	// Which fused kernel family serves whole-tile groups: 2 = automatic (default): the two-stage duo kernel,
 	// or the four-stage quartet pipeline when the group has too few tiles to fill the GPU (and for
 	// signatures that only have a quartet entry); 3 = quartet wherever it exists; 4 = duo wherever it exists;
-	// 1 = quad, 0 = the plain thread-per-stream twin.  OALSFX_KERNEL=auto|quartet|duo|quad|single overrides
+	// 1 = quad, 0 = the plain thread-per-stream twin, 5 = the relay pipeline wherever eligible.
+	// OALSFX_KERNEL=auto|quartet|duo|quad|single|relay overrides
 	// (A/B measurements and the parity tests of every family).
 	int family = 2;
 	// Host-buffer mix: tile slice the next launches are restricted to (0 = all tiles), and the
@@ -637,6 +638,40 @@ struct oalsfx_engine {
 				any_filter = true; // keeps the group on the exact (generic) kernels, see coefs.h
 			}
 		}
+		// The relay pipeline (relay.cuh): any signature of two or more effects in one launch, one warp per effect.
+		const bool whole_tiles_group = g.identity || g.full_tiles;
+		int active = 0;
+		for (int s = 0; s < kMaxSlots; ++s) {
+			active += kinds[s] != kKindNull ? 1 : 0;
+		}
+		const bool relay_ok = be->has_relay() && !any_filter && frames >= 2 && whole_tiles_group &&
+			(channels == 1 || channels == 2) && active >= 2 && family != 0;
+		auto launch_relay = [&]() {
+			MixArgs a;
+			fill_common(a, g, frames, src, dst, layout, frames_total, frame0);
+			a.with_dry = 1;
+			int pos = 0, floats = 0;
+			bool heavy = false;
+			for (int s = 0; s < kMaxSlots; ++s) {
+				if (kinds[s] == kKindNull) {
+					continue;
+				}
+				fill_slot(a, g, pos, s, first_block);
+				a.relay_kind[pos] = kinds[s];
+				a.relay_win[pos] = floats;
+				floats += kinds[s] == kKindReverb ? kPfWarpFloats : (kinds[s] == kKindModDelay || kinds[s] == kKindEcho) ? kFwWarpFloats : 0;
+				heavy = heavy || kinds[s] == kKindReverb;
+				++pos;
+			}
+			a.relay_count = pos;
+			a.relay_smem_floats = floats;
+			sanitize_gains(a);
+			++launches;
+			return be->launch_mix(channels == 1 ? (heavy ? kRelayMonoHeavy : kRelayMono) : (heavy ? kRelayStereoHeavy : kRelayStereo), a, stream);
+		};
+		if (relay_ok && family == 5) { // OALSFX_KERNEL=relay: wherever eligible (A/B measurements, parity tests)
+			return launch_relay();
+		}
 		// A fused single-pass kernel for this signature?
 		const KernelInfo* infos = kernel_infos();
 		for (int k = 0; k < kKernelCount; ++k) {
@@ -646,6 +681,16 @@ struct oalsfx_engine {
 			}
 			if (std::memcmp(ki.kind, kinds, sizeof(kinds)) != 0) {
 				continue;
+			}
+			// A signature whose only fused kernel is the thread-per-stream one (cfg3's flanger + ring modulator +
+			// distortion + compressor): below ~1000 tiles a stream's serial per-sample work bounds the block, and
+			// the relay pipeline (a warp per effect) halves it -- B200, ms per 1024-frame block, mono 96 kHz:
+			// 32 tiles 0.58 vs 1.08, 512 tiles 0.76 vs 1.40; 2048 tiles 2.34 vs 1.83 (throughput-bound: fewer
+			// instructions win).
+			constexpr int kRelayMaxTiles = 1024;
+			if (relay_ok && family == 2 && duo_for_twin(ki.id) < 0 && quartet_for_twin(ki.id) < 0 &&
+				(slice_count > 0 ? slice_count : g.tile_count) <= kRelayMaxTiles) {
+				return launch_relay();
 			}
 			MixArgs a;
 			fill_common(a, g, frames, src, dst, layout, frames_total, frame0);
@@ -679,6 +724,9 @@ struct oalsfx_engine {
 				id = quad_for_twin(ki.id);
 			}
 			return be->launch_mix(id, a, stream);
+		}
+		if (relay_ok) {
+			return launch_relay();
 		}
 		// Chain of single-effect passes: the dry pass carries the first non-null slot.
 		static const int gen_for_kind[] = {kGenDry, kGenModDelay, kGenCompressor, kGenDedicated, kGenDistortion,
@@ -750,7 +798,7 @@ int oalsfx_engine_create(const oalsfx_engine_desc* desc, oalsfx_engine** out)
 	e->channels = dev.channels;
 	e->slots = desc->effect_count;
 	if (const char* fam = std::getenv("OALSFX_KERNEL")) {
-		e->family = (std::strcmp(fam, "single") == 0 ? 0 : std::strcmp(fam, "quad") == 0 ? 1 : std::strcmp(fam, "quartet") == 0 ? 3 : std::strcmp(fam, "duo") == 0 ? 4 : 2);
+		e->family = (std::strcmp(fam, "single") == 0 ? 0 : std::strcmp(fam, "quad") == 0 ? 1 : std::strcmp(fam, "quartet") == 0 ? 3 : std::strcmp(fam, "duo") == 0 ? 4 : std::strcmp(fam, "relay") == 0 ? 5 : 2);
 	}
 	e->be = make_backend(desc->device, g_create_error);
 	if (!e->be) {

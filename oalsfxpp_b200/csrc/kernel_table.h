@@ -69,6 +69,14 @@
 	TBX(kTabRingMod, FxRingMod, kKindRingMod) \
 	TBX(kTabReverb, FxReverb, kKindReverb)
 
+// Relay kernels (relay.cuh): any slot signature as a warp pipeline, one warp per non-null slot, the effect of
+// each stage chosen at run time.  RX(id, CT, HEAVY): HEAVY = the reverb is compiled in.
+#define OALSFX_RELAY_TABLE(RX) \
+	RX(kRelayMono, 1, false) \
+	RX(kRelayStereo, 2, false) \
+	RX(kRelayMonoHeavy, 1, true) \
+	RX(kRelayStereoHeavy, 2, true)
+
 namespace oalsfx {
 
 enum KernelId : int {
@@ -89,6 +97,9 @@ enum KernelId : int {
 #define OALSFX_TBX(id, Fx, kind) id,
 	OALSFX_TABMODE_TABLE(OALSFX_TBX)
 #undef OALSFX_TBX
+#define OALSFX_RX(id, CT, HEAVY) id,
+	OALSFX_RELAY_TABLE(OALSFX_RX)
+#undef OALSFX_RX
 	kKernelEnd
 };
 
@@ -204,6 +215,9 @@ inline const char* kernel_name(int id)
 #define OALSFX_TBX(tid, Fx, kind) if (id == tid) return #tid;
 	OALSFX_TABMODE_TABLE(OALSFX_TBX)
 #undef OALSFX_TBX
+#define OALSFX_RX(rid, CT, HEAVY) if (id == rid) return #rid;
+	OALSFX_RELAY_TABLE(OALSFX_RX)
+#undef OALSFX_RX
 	return "?";
 }
 

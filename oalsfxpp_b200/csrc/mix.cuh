@@ -58,6 +58,11 @@ struct MixArgs {
 	const int32_t* lane_class[kMaxSlots];
 	const SendCoef* send_table;
 	const int32_t* lane_send;
+	// Relay kernels (relay.cuh): slot position p = pipeline stage p (non-null slots, compacted in slot order).
+	int32_t relay_count;              // stages
+	int32_t relay_kind[kMaxSlots];    // FxKind of stage p
+	int32_t relay_win[kMaxSlots];     // stage p's prefetch window: float offset into the dynamic shared memory
+	int32_t relay_smem_floats;        // dynamic shared memory of the launch
 };
 
 // Send shelf filters (reference: apply_filters, oalsfxpp.cpp:3101-3143).  Pass-through still

@@ -1,0 +1,252 @@
+// relay.cuh -- ANY slot signature as a warp pipeline: one warp per non-null effect slot of a 32-stream tile.
+//
+// The fused duo / quartet kernels are compiled per signature (equalizer + chorus + echo + reverb, a single
+// reverb ...).  Every other combination of the ten effect types used to run as a chain of single-effect
+// passes: one launch per slot, each re-reading the input and read-modify-writing the output in HBM, and one
+// warp per tile doing a long dependent instruction sequence per sample.  The relay kernel covers all of them
+// in ONE launch and ONE pass over the I/O buffers:
+//
+//   stage 0          : input frame (cp.async window), dry mix (direct send), first non-null slot
+//   stage 1 .. n-1   : the next non-null slots, in slot order
+//   last stage       : + output rows
+//
+// The effect a stage runs is chosen at run time (MixArgs::relay_kind, one warp-uniform switch per launch),
+// the stage POSITION is a template parameter so that its coefficient block a.slot[P] stays a constant-bank
+// operand.  A stage hands the input frame and the running output bus to the next one through a double-
+// buffered shared-memory exchange of kChunk frames guarded by named barriers (the protocol of quartet.cuh),
+// so per output sample the additions happen in the reference's order: dry, then slot by slot
+// (oalsfxpp.cpp:2984-3037).  Slots are parallel aux sends of the same source, so a
+// stage needs nothing from its predecessor but those two vectors.
+//
+// LIGHT kernels leave the reverb out (128 registers, 4 CTAs per SM); HEAVY ones (any reverb among the slots)
+// run the unsplit reverb in one warp with its batched cp.async window (up to 255 registers).  Windows live in
+// dynamic shared memory at host-computed offsets (MixArgs::relay_win), so a launch only pays for the windows
+// its own effects use.
+//
+// Host-checked requirements (as for the duo kernels): no send shelf filter active, no unstable filter,
+// frames >= 2, every tile of the launch takes part with all of its lanes, sanitized static gains,
+// one or two device channels.
+#ifndef OALSFX_RELAY_CUH
+#define OALSFX_RELAY_CUH
+
+#if defined(__CUDACC__)
+
+#include "kernel_table.h"
+#include "quartet.cuh"
+
+namespace oalsfx {
+namespace relay {
+
+constexpr int kChunk = 4;                 // frames per hand-off (= the output row batch)
+constexpr int kThreads = kMaxSlots * kLanes;
+
+template <int CT>
+struct Shared {
+	float xch[kMaxSlots][2][kChunk][2 * CT][kLanes]; // hand-off P -> P+1: x_0..x_C-1, bus_0..bus_C-1 (the last stage parks finished frames in its own)
+	float win_in[kFwSlots][CT][kLanes];              // stage 0: input frames in flight
+};
+
+template <int CT, int P, class Fx>
+__device__ __forceinline__ void stage(const MixArgs& a, Shared<CT>& sh, float* dyn, const int tile, const int lane)
+{
+	constexpr bool kReverb = std::is_same<Fx, FxReverb>::value;
+	constexpr bool kMod = std::is_same<Fx, FxModDelay>::value;
+	constexpr bool kEcho = std::is_same<Fx, FxEcho>::value;
+	constexpr int HP = P > 0 ? P - 1 : 0;           // hand-off this stage reads
+	constexpr int HN = P < kMaxSlots - 1 ? P : 0;   // hand-off this stage writes (unless it is the last)
+	const bool last = P + 1 == a.relay_count;       // warp-uniform
+	const bool io_ok = tile * kLanes + lane < a.num_streams;
+	const float* src = a.src + tile * a.io_ts + lane * a.io_ls;
+	float* dst = a.dst + tile * a.io_ts + lane * a.io_ls;
+	uint32_t* ss = a.send_state + (static_cast<long long>(tile) * kSendStateWords) * kLanes + lane;
+	const int chunks = (a.frames + kChunk - 1) / kChunk;
+	const bool fast_out = a.io_cs == 1 && a.io_fs == CT && (a.frames % kChunk) == 0 && (a.io_ls % 4) == 0 &&
+		(a.io_ts % 4) == 0 && (reinterpret_cast<unsigned long long>(a.dst) & 15ULL) == 0;
+
+	SlotRunner<CT, false, Fx> r;
+	float* win = dyn + a.relay_win[P];
+	r.begin(a, P, tile, lane, (kReverb || kMod) ? win + lane : kEcho ? win + lane + 2 * kLanes : nullptr);
+
+	// Stage 0 input.  Through the cp.async window, kFwDepth frames ahead, in the same commit groups as the
+	// effect's own ring prefetches; a reverb runs its own cp.async pipeline inside step(), so there the frames
+	// of the next hand-off are loaded into registers one hand-off early and parked in the same window.
+	const unsigned win_s = smem_addr(&sh.win_in[0][0][lane]);
+	const float* in = src;
+	auto issue_input = [&](int frame) {
+		if (P == 0 && !kReverb) {
+			if (io_ok && frame < a.frames) {
+				const unsigned slot = win_s + static_cast<unsigned>((frame & (kFwSlots - 1)) * CT * kLanes * 4);
+#pragma unroll
+				for (int c = 0; c < CT; ++c) {
+					cp_async_f32_s(slot + c * kLanes * 4, in + c * a.io_cs);
+				}
+			}
+			in += a.io_fs;
+		}
+	};
+	float nx[kChunk][CT];
+	auto load_rows = [&](int first) {
+#pragma unroll
+		for (int f = 0; f < kChunk; ++f) {
+#pragma unroll
+			for (int c = 0; c < CT; ++c) {
+				nx[f][c] = (io_ok && first + f < a.frames) ? src[(first + f) * a.io_fs + c * a.io_cs] : 0.0F;
+			}
+		}
+	};
+	if (P == 0 && kReverb) {
+		load_rows(0);
+	}
+	if (!kReverb) {
+		for (int k = 0; k < kFwDepth; ++k) {
+			r.fx.prefetch_issue(a.slot[P], k);
+			issue_input(k);
+			cp_async_commit_group();
+		}
+	}
+	if (P > 0) {
+		quartet::signal_empty<HP>(0);
+		quartet::signal_empty<HP>(1);
+	}
+	for (int ci = 0; ci < chunks; ++ci) {
+		const int b = ci & 1;
+		const int first = ci * kChunk;
+		const int count = min(kChunk, a.frames - first);
+		if (P == 0 && kReverb) {
+			// this hand-off's frames go to the thread's own window column, the next one's are requested
+#pragma unroll
+			for (int f = 0; f < kChunk; ++f) {
+#pragma unroll
+				for (int c = 0; c < CT; ++c) {
+					sh.win_in[(first + f) & (kFwSlots - 1)][c][lane] = nx[f][c];
+				}
+			}
+			load_rows(first + kChunk);
+		}
+		if (P > 0) {
+			quartet::wait_full<HP>(b);
+		}
+		if (P < kMaxSlots - 1 && !last) {
+			quartet::wait_empty<HN>(b);
+		}
+		for (int f = 0; f < count; ++f) {
+			{
+				const int i = first + f;
+				float x[CT], acc[CT];
+				if (!kReverb) {
+					r.fx.prefetch_next(a.slot[P]);
+					issue_input(i + kFwDepth);
+					cp_async_commit_group();
+					cp_async_wait_group<kFwDepth>();
+				}
+				if (P == 0) {
+#pragma unroll
+					for (int c = 0; c < CT; ++c) {
+						x[c] = io_ok ? sh.win_in[i & (kFwSlots - 1)][c][lane] : 0.0F;
+						acc[c] = 0.0F;
+					}
+					// direct send (oalsfxpp.cpp:2924-2950); gains sanitized by the host
+#pragma unroll
+					for (int c = 0; c < CT; ++c) {
+						pan_add<CT, true>(acc, CT, a.direct.gains[c], x[c]);
+					}
+				} else {
+#pragma unroll
+					for (int c = 0; c < CT; ++c) {
+						x[c] = sh.xch[HP][b][f][c][lane];
+						acc[c] = sh.xch[HP][b][f][CT + c][lane];
+					}
+				}
+				r.step(a, P, x, acc);
+				if (last && !fast_out) {
+					if (io_ok) {
+#pragma unroll
+						for (int c = 0; c < CT; ++c) {
+							dst[i * a.io_fs + c * a.io_cs] = acc[c];
+						}
+					}
+				} else {
+#pragma unroll
+					for (int c = 0; c < CT; ++c) {
+						if (!last) {
+							sh.xch[P][b][f][c][lane] = x[c];
+						}
+						sh.xch[P][b][f][CT + c][lane] = acc[c];
+					}
+				}
+			}
+		}
+		if (last) {
+			if (fast_out && io_ok) {
+				// kChunk frames x CT channels of this thread's row, 16 bytes at a time (own column: no barrier)
+				float4* row = reinterpret_cast<float4*>(dst + first * CT);
+#pragma unroll
+				for (int g = 0; g < kChunk * CT / 4; ++g) {
+					const int e0 = 4 * g; // element index within the chunk: frame = e / CT, channel = e % CT
+					__stcs(row + g, make_float4(sh.xch[P][b][(e0 + 0) / CT][CT + (e0 + 0) % CT][lane], sh.xch[P][b][(e0 + 1) / CT][CT + (e0 + 1) % CT][lane],
+						sh.xch[P][b][(e0 + 2) / CT][CT + (e0 + 2) % CT][lane], sh.xch[P][b][(e0 + 3) / CT][CT + (e0 + 3) % CT][lane]));
+				}
+			}
+		} else if (P < kMaxSlots - 1) {
+			__threadfence_block();
+			quartet::signal_full<HN>(b);
+		}
+		if (P > 0 && ci + 2 < chunks) {
+			quartet::signal_empty<HP>(b); // nobody waits for the last two drains
+		}
+	}
+	if (!kReverb) {
+		cp_async_wait_group<0>();
+	}
+	r.end_state_only(a, P, tile, lane);
+	if (P == 0) {
+		duo::store_passthrough_history<CT>(ss, 0, src, a, io_ok);
+	}
+	duo::store_passthrough_history<CT>(ss, 1 + a.aux_index[P], src, a, io_ok);
+}
+
+template <int CT, bool HEAVY, int P>
+__device__ __forceinline__ void dispatch(const MixArgs& a, Shared<CT>& sh, float* dyn, int tile, int lane)
+{
+	switch (a.relay_kind[P]) {
+	case kKindModDelay: stage<CT, P, FxModDelay>(a, sh, dyn, tile, lane); break;
+	case kKindCompressor: stage<CT, P, FxCompressor>(a, sh, dyn, tile, lane); break;
+	case kKindDedicated: stage<CT, P, FxDedicated>(a, sh, dyn, tile, lane); break;
+	case kKindDistortion: stage<CT, P, FxDistortion>(a, sh, dyn, tile, lane); break;
+	case kKindEcho: stage<CT, P, FxEcho>(a, sh, dyn, tile, lane); break;
+	case kKindEqualizer: stage<CT, P, FxEqualizer>(a, sh, dyn, tile, lane); break;
+	case kKindRingMod: stage<CT, P, FxRingMod>(a, sh, dyn, tile, lane); break;
+	case kKindReverb:
+		if (HEAVY) {
+			stage<CT, P, typename std::conditional<HEAVY, FxReverb, FxDedicated>::type>(a, sh, dyn, tile, lane);
+		}
+		break;
+	default: break;
+	}
+}
+
+template <int CT, bool HEAVY>
+__global__ void __launch_bounds__(kThreads, HEAVY ? 2 : 4) relay_kernel(const __grid_constant__ MixArgs a)
+{
+	extern __shared__ __align__(16) float dyn[];
+	__shared__ __align__(16) Shared<CT> sh;
+	const int tile = a.tiles ? static_cast<int>(a.tiles[blockIdx.x].tile) : a.tile_first + static_cast<int>(blockIdx.x);
+	const int lane = threadIdx.x % kLanes;
+	// Warp w of every CTA lands on scheduler w: rotate the stages so each scheduler sees all of them.
+	const int st = (static_cast<int>(threadIdx.x / kLanes) + static_cast<int>(blockIdx.x)) & (kMaxSlots - 1);
+	if (st >= a.relay_count) {
+		return;
+	}
+	switch (st) {
+	case 0: dispatch<CT, HEAVY, 0>(a, sh, dyn, tile, lane); break;
+	case 1: dispatch<CT, HEAVY, 1>(a, sh, dyn, tile, lane); break;
+	case 2: dispatch<CT, HEAVY, 2>(a, sh, dyn, tile, lane); break;
+	default: dispatch<CT, HEAVY, 3>(a, sh, dyn, tile, lane); break;
+	}
+}
+
+} // namespace relay
+} // namespace oalsfx
+
+#endif // __CUDACC__
+#endif

@@ -153,7 +153,7 @@ def test_cfg2_schedule_on_4096_streams(checker):
         _assert_match(expect, y[s], True, f"stream {s}")
 
 
-@pytest.mark.parametrize("family", ["quartet", "duo", "quad", "single"])
+@pytest.mark.parametrize("family", ["quartet", "duo", "quad", "single", "relay"])
 def test_every_kernel_family_on_the_chain(checker, family, monkeypatch):
     """The fused 4-slot stereo chain has four implementations (OALSFX_KERNEL, read when an engine is
     created): the two-stage duo kernel (default), the four-stage quartet pipeline, the 4-lanes-per-stream
@@ -292,6 +292,95 @@ def test_every_kernel_family_on_the_single_reverb_slot(checker, family, fmt, mon
     for s in (0, 31, 32, 95):
         expect = H.run_script_orc(checker, fmt, 48000, 1, script, x[s])
         _assert_match(expect, y[s], True, f"{family} stream {s}")
+
+
+RELAY_SIGNATURES = [
+    # (format, rate, slots) -- none of these has a fused kernel of its own: the relay pipeline runs them in one launch
+    (F.stereo, 48000, [T.echo, T.eax_reverb]),
+    (F.stereo, 48000, [T.eax_reverb, T.chorus, T.reverb, T.compressor]),       # reverb in stage 0, two reverbs
+    (F.stereo, 48000, [T.distortion, T.null, T.flanger, T.equalizer]),          # a null slot in the middle
+    (F.stereo, 44100, [T.ring_modulator, T.dedicated_dialog, T.echo, T.chorus]),
+    (F.mono, 48000, [T.chorus, T.echo]),
+    (F.mono, 96000, [T.equalizer, T.distortion, T.compressor, T.dedicated_low_frequency]),
+    (F.mono, 48000, [T.null, T.reverb, T.echo, T.flanger]),
+    (F.stereo, 48000, [T.compressor, T.equalizer, T.null, T.null]),
+]
+
+
+@pytest.mark.parametrize("sig", range(len(RELAY_SIGNATURES)))
+def test_relay_pipeline_runs_any_signature_in_one_launch(checker, sig):
+    """relay.cuh: one warp per non-null slot, effect per stage chosen at run time.  Signatures without a fused
+    kernel, parameter changes (ramps / cross-fades / filter steps) in block 2, block sizes that are not a
+    multiple of the hand-off, a ragged last tile.  One launch per block, bit-exact against the checker
+    (ring modulator: device sinf, 1e-5)."""
+    fmt, rate, slots = RELAY_SIGNATURES[sig]
+    lib = _lib()
+    C = 1 if fmt == F.mono else 2
+    S, blocks = 70, [1024, 333, 1024, 2, 641]
+    total = sum(blocks)
+    x = np.stack([H.noise(900 + 10 * sig + s, C, total) for s in range(S)])
+    y = np.empty_like(x)
+
+    def changed(t):
+        if t in (T.eax_reverb, T.reverb):
+            return ox.default_props(t, lib=lib, gain_=0.2, reflections_delay_=0.012, decay_time_=2.5)
+        if t == T.equalizer:
+            return ox.default_props(t, lib=lib, mid1_gain_=1.7)
+        if t == T.echo:
+            return ox.default_props(t, lib=lib, delay_=0.05, feedback_=0.7)
+        if t in (T.chorus, T.flanger):
+            return ox.default_props(t, lib=lib, depth_=0.5, feedback_=-0.4)
+        if t == T.distortion:
+            return ox.default_props(t, lib=lib, edge_=0.7)
+        if t == T.ring_modulator:
+            return ox.default_props(t, lib=lib, frequency_=1000.0)
+        return None
+
+    script = [("type", i, t) for i, t in enumerate(slots)] + [("apply",)]
+    with ox.Engine(S, fmt, rate, len(slots), lib=lib) as eng:
+        for i, t in enumerate(slots):
+            eng.set_effect(i, t)
+        at = 0
+        for b, n in enumerate(blocks):
+            if b == 2:
+                for i, t in enumerate(slots):
+                    p = changed(t)
+                    if p is not None:
+                        eng.set_effect(i, t, p)
+                        script += [("props", i, p)]
+                script += [("apply",)]
+            script += [("mix", n)]
+            y[:, at:at + n] = eng.mix(np.ascontiguousarray(x[:, at:at + n]))
+            at += n
+        assert eng.launch_count == len(blocks), eng.launch_count
+    exact = T.ring_modulator not in slots
+    for s in (0, 31, 32, 63, 64, S - 1):
+        expect = H.run_script_orc(checker, fmt, rate, len(slots), script, x[s])
+        _assert_match(expect, y[s], exact, f"relay signature {sig} stream {s}")
+
+
+def test_relay_pipeline_on_the_cfg3_chain(checker, monkeypatch):
+    """cfg3's signature (flanger + ring modulator + distortion + compressor, mono, 96 kHz) has a fused
+    thread-per-stream kernel; OALSFX_KERNEL=relay runs it as a four-warp pipeline instead."""
+    monkeypatch.setenv("OALSFX_KERNEL", "relay")
+    lib = _lib()
+    slots = [T.flanger, T.ring_modulator, T.distortion, T.compressor]
+    S, blocks = 96, [1024, 1024, 500]
+    total = sum(blocks)
+    x = np.stack([H.noise(1300 + s, 1, total) for s in range(S)])
+    y = np.empty_like(x)
+    script = H.simple_script([(t, None) for t in slots], blocks)
+    with ox.Engine(S, F.mono, 96000, 4, lib=lib) as eng:
+        for i, t in enumerate(slots):
+            eng.set_effect(i, t)
+        at = 0
+        for n in blocks:
+            y[:, at:at + n] = eng.mix(np.ascontiguousarray(x[:, at:at + n]))
+            at += n
+        assert eng.launch_count == len(blocks)
+    for s in (0, 31, 32, 95):
+        expect = H.run_script_orc(checker, F.mono, 96000, 4, script, x[s])
+        _assert_match(expect, y[s], False, f"relay cfg3 stream {s}")
 
 
 def test_full_size_chain_device_buffers(checker):
