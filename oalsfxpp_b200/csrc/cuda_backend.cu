@@ -16,6 +16,7 @@
 #include "duo.cuh"
 #include "quartet.cuh"
 #include "relay.cuh"
+#include "span.cuh"
 
 namespace oalsfx {
 namespace {
@@ -350,6 +351,16 @@ public:
 				static_cast<size_t>(args.relay_smem_floats) * sizeof(float), st>>>(args); break;
 			OALSFX_RELAY_TABLE(OALSFX_RX)
 #undef OALSFX_RX
+#define OALSFX_SX(id, CT) \
+		case id: \
+			if (!carveout_done_[id]) { \
+				cudaFuncSetAttribute(span::span_reverb_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, span::shared_floats(CT) * static_cast<int>(sizeof(float))); \
+				carveout_done_[id] = true; \
+			} \
+			span::span_reverb_kernel<CT><<<static_cast<unsigned>(args.tile_count), span::kThreads, \
+				static_cast<size_t>(span::shared_floats(CT)) * sizeof(float), st>>>(args); break;
+			OALSFX_SPAN_TABLE(OALSFX_SX)
+#undef OALSFX_SX
 		default:
 			error_ = "unknown kernel id";
 			return false;

@@ -27,6 +27,7 @@
 #include "backend.h"
 #include "derive.h"
 #include "kernel_table.h"
+#include "span.cuh"
 
 using namespace oalsfx;
 
@@ -114,7 +115,7 @@ struct oalsfx_engine {
 	// or the four-stage quartet pipeline when the group has too few tiles to fill the GPU (and for
 	// signatures that only have a quartet entry); 3 = quartet wherever it exists; 4 = duo wherever it exists;
 	// 1 = quad, 0 = the plain thread-per-stream twin, 5 = the relay pipeline wherever eligible.
-	// OALSFX_KERNEL=auto|quartet|duo|quad|single|relay overrides
+	// 6 = as automatic (names the span kernel's tests).  OALSFX_KERNEL=auto|quartet|duo|quad|single|relay|span overrides
 	// (A/B measurements and the parity tests of every family).
 	int family = 2;
 	// Host-buffer mix: tile slice the next launches are restricted to (0 = all tiles), and the
@@ -705,6 +706,17 @@ struct oalsfx_engine {
 			sanitize_gains(a);
 			const bool whole_tiles = g.identity || g.full_tiles;
 			int id = ki.id;
+			// The single-reverb-slot signature with few tiles: block-parallel in time (span.cuh) whenever no update
+			// is pending and the preset's delays allow a span (the device verifies the stream state and falls back).
+			constexpr int kSpanMaxTiles = 160;
+			if ((ki.id == kReverbMono || ki.id == kReverbStereo) && whole_tiles && be->has_relay() && (family == 2 || family == 6) &&
+				a.update_mask == 0 && a.tile_count <= kSpanMaxTiles && slice_count == 0) {
+				const int t = span::span_frames_for(a.slot[0].u.reverb);
+				if (t > 0) {
+					a.span_frames = t;
+					return be->launch_mix(ki.id == kReverbMono ? kSpanReverbMono : kSpanReverbStereo, a, stream);
+				}
+			}
 			// Few tiles cannot fill the GPU with two warps each: below ~one tile per SM the four-stage pipeline
 			// (twice the warps per tile) wins -- measured on B200, 4-slot stereo chain, ms per 1024-frame block:
 			// 128 tiles 0.47 (quartet) vs 0.63 (duo); 256 tiles 0.64 vs 0.64; 2048 tiles 3.6 vs 3.07.
@@ -798,7 +810,7 @@ int oalsfx_engine_create(const oalsfx_engine_desc* desc, oalsfx_engine** out)
 	e->channels = dev.channels;
 	e->slots = desc->effect_count;
 	if (const char* fam = std::getenv("OALSFX_KERNEL")) {
-		e->family = (std::strcmp(fam, "single") == 0 ? 0 : std::strcmp(fam, "quad") == 0 ? 1 : std::strcmp(fam, "quartet") == 0 ? 3 : std::strcmp(fam, "duo") == 0 ? 4 : std::strcmp(fam, "relay") == 0 ? 5 : 2);
+		e->family = (std::strcmp(fam, "single") == 0 ? 0 : std::strcmp(fam, "quad") == 0 ? 1 : std::strcmp(fam, "quartet") == 0 ? 3 : std::strcmp(fam, "duo") == 0 ? 4 : std::strcmp(fam, "relay") == 0 ? 5 : std::strcmp(fam, "span") == 0 ? 6 : 2);
 	}
 	e->be = make_backend(desc->device, g_create_error);
 	if (!e->be) {

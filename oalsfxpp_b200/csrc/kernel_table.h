@@ -77,6 +77,11 @@
 	RX(kRelayMonoHeavy, 1, true) \
 	RX(kRelayStereoHeavy, 2, true)
 
+// Span kernels (span.cuh): the single-reverb-slot signature block-parallel in time.  SX(id, CT).
+#define OALSFX_SPAN_TABLE(SX) \
+	SX(kSpanReverbMono, 1) \
+	SX(kSpanReverbStereo, 2)
+
 namespace oalsfx {
 
 enum KernelId : int {
@@ -100,6 +105,9 @@ enum KernelId : int {
 #define OALSFX_RX(id, CT, HEAVY) id,
 	OALSFX_RELAY_TABLE(OALSFX_RX)
 #undef OALSFX_RX
+#define OALSFX_SX(id, CT) id,
+	OALSFX_SPAN_TABLE(OALSFX_SX)
+#undef OALSFX_SX
 	kKernelEnd
 };
 
@@ -218,6 +226,9 @@ inline const char* kernel_name(int id)
 #define OALSFX_RX(rid, CT, HEAVY) if (id == rid) return #rid;
 	OALSFX_RELAY_TABLE(OALSFX_RX)
 #undef OALSFX_RX
+#define OALSFX_SX(sid, CT) if (id == sid) return #sid;
+	OALSFX_SPAN_TABLE(OALSFX_SX)
+#undef OALSFX_SX
 	return "?";
 }
 

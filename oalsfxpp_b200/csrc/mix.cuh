@@ -63,6 +63,8 @@ struct MixArgs {
 	int32_t relay_kind[kMaxSlots];    // FxKind of stage p
 	int32_t relay_win[kMaxSlots];     // stage p's prefetch window: float offset into the dynamic shared memory
 	int32_t relay_smem_floats;        // dynamic shared memory of the launch
+	// Span kernels (span.cuh): frames per block-parallel span (host-checked against every delay of slot[0])
+	int32_t span_frames;
 };
 
 // Send shelf filters (reference: apply_filters, oalsfxpp.cpp:3101-3143).  Pass-through still

@@ -20,7 +20,7 @@ from oalsfxpp_b200 import ChannelFormat as F, EffectType as T  # noqa: E402
 BLOCK = 1024
 
 
-def run(name, streams, fmt, rate, chain, bytes_per_frame, schedule=None, blocks=24, warm=4):
+def run(name, streams, fmt, rate, chain, bytes_per_frame, schedule=None, blocks=24, warm=4, setup=None):
     channels = ox.channel_count(fmt)
     dev = torch.device("cuda:0")
     x = (torch.rand(streams, BLOCK, channels, device=dev) - 0.5)
@@ -29,6 +29,8 @@ def run(name, streams, fmt, rate, chain, bytes_per_frame, schedule=None, blocks=
     with ox.Engine(streams, fmt, rate, len(chain)) as eng:
         for i, t in enumerate(chain):
             eng.set_effect(i, t)
+        if setup:
+            setup(eng)
         host_s = 0.0
         times = []
         for b in range(warm + blocks):
@@ -60,6 +62,24 @@ def cfg2_schedule(eng, b):
     eng.set_effect(0, T.equalizer, eq)
 
 
+def all_presets(eng):
+    """Slot 3: stream s gets reverb preset s mod 113 -- 113 parameter classes in one engine (table mode)."""
+    names = ox.reverb_preset_names()
+    per = [ox.reverb_preset(g, n) for g, n in names]
+    for i, p in enumerate(per):
+        # streams i, i + 113, ... : set in strided runs of one stream is slow from Python; use blocks of streams instead
+        pass
+    n = eng.num_streams
+    chunk = max(1, n // (len(per) * 8))
+    s = 0
+    k = 0
+    while s < n:
+        m = min(chunk, n - s)
+        eng.set_effect(3, T.eax_reverb, per[k % len(per)], first_stream=s, n_streams=m)
+        s += m
+        k += 1
+
+
 def main():
     out = [
         run("cfg1: EAX reverb, 1024 mono streams", 1024, F.mono, 48000, [T.eax_reverb], 200),
@@ -70,6 +90,15 @@ def main():
             [T.flanger, T.ring_modulator, T.distortion, T.compressor], 24),
         run("cfg4: EQ+chorus+echo+EAX, 65536 stereo streams", 65536, F.stereo, 48000,
             [T.equalizer, T.chorus, T.echo, T.eax_reverb], 236, blocks=10, warm=3),
+        # signatures without a fused kernel of their own: the relay pipeline (one launch, a warp per slot)
+        run("relay: echo+EAX, 65536 stereo streams", 65536, F.stereo, 48000, [T.echo, T.eax_reverb], 220, blocks=10, warm=3),
+        run("relay: EAX+chorus+reverb+compressor, 4096 stereo streams", 4096, F.stereo, 48000,
+            [T.eax_reverb, T.chorus, T.reverb, T.compressor], 416),
+        run("relay: distortion+flanger+equalizer, 65536 stereo streams", 65536, F.stereo, 48000,
+            [T.distortion, T.flanger, T.equalizer], 32, blocks=10, warm=3),
+        # every stream its own reverb preset (113 parameter classes): table mode, coefficient blocks from HBM
+        run("table mode: cfg4 chain, 113 reverb presets over 16384 stereo streams", 16384, F.stereo, 48000,
+            [T.equalizer, T.chorus, T.echo, T.eax_reverb], 236, blocks=10, warm=3, setup=all_presets),
     ]
     print(json.dumps({"gpu": torch.cuda.get_device_name(0), "block_frames": BLOCK, "results": out}, indent=1))
 

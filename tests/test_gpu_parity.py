@@ -265,7 +265,7 @@ def test_pipelined_kernels_under_load_are_race_free(checker, family, monkeypatch
 
 
 @pytest.mark.parametrize("fmt", [F.mono, F.stereo])
-@pytest.mark.parametrize("family", ["quartet", "quad", "single"])
+@pytest.mark.parametrize("family", ["quartet", "quad", "single", "span"])
 def test_every_kernel_family_on_the_single_reverb_slot(checker, family, fmt, monkeypatch):
     """cfg1's signature (one reverb slot, mono): pipeline (default), quad and plain kernels, with a preset
     change mid-stream (tap cross-fade + gain ramp), a modulated preset and odd block sizes."""
@@ -292,6 +292,42 @@ def test_every_kernel_family_on_the_single_reverb_slot(checker, family, fmt, mon
     for s in (0, 31, 32, 95):
         expect = H.run_script_orc(checker, fmt, 48000, 1, script, x[s])
         _assert_match(expect, y[s], True, f"{family} stream {s}")
+
+
+@pytest.mark.parametrize("case", ["eax-mono", "eax-stereo", "standard-96k", "forest", "short-first-blocks", "dense"])
+def test_span_kernel_on_steady_state_blocks(checker, case):
+    """span.cuh: blocks without a pending update run the single reverb slot block-parallel in time (spans of
+    up to 64 frames, recurrences in dedicated warps).  Steady-state blocks of odd sizes after a preset change,
+    a ragged last tile, presets with short delay lines, and blocks so short that the tap cross-fade is still
+    running when the next block starts (the device-side check sends those to the exact serial body)."""
+    lib = _lib()
+    fmt = F.mono if case in ("eax-mono", "short-first-blocks") else F.stereo
+    rate = 96000 if case == "standard-96k" else 48000
+    rtype = T.reverb if case == "standard-96k" else T.eax_reverb
+    first = {"forest": ox.reverb_preset("Default", "forest", lib=lib),
+             "dense": ox.default_props(rtype, lib=lib, density_=0.0, diffusion_=1.0, reflections_delay_=0.002, late_reverb_delay_=0.003)}.get(case)
+    second = ox.default_props(rtype, lib=lib, gain_=0.5, decay_time_=3.0, reflections_delay_=0.02)
+    blocks = [50, 30, 70, 1024, 333] if case == "short-first-blocks" else [1024, 1024, 777, 64, 2, 1500, 1024]
+    change_at = 4 if case != "short-first-blocks" else 99
+    S = 70
+    C = ox.channel_count(fmt)
+    total = sum(blocks)
+    x = np.stack([H.noise(2000 + s, C, total) for s in range(S)])
+    y = np.empty_like(x)
+    script = [("type", 0, rtype)] + ([("props", 0, first)] if first is not None else []) + [("apply",)]
+    with ox.Engine(S, fmt, rate, 1, lib=lib) as eng:
+        eng.set_effect(0, rtype, first)
+        at = 0
+        for b, n in enumerate(blocks):
+            if b == change_at:
+                eng.set_effect(0, rtype, second)
+                script += [("props", 0, second), ("apply",)]
+            script += [("mix", n)]
+            y[:, at:at + n] = eng.mix(np.ascontiguousarray(x[:, at:at + n]))
+            at += n
+    for s in (0, 31, 32, 63, 64, S - 1):
+        expect = H.run_script_orc(checker, fmt, rate, 1, script, x[s])
+        _assert_match(expect, y[s], True, f"span {case} stream {s}")
 
 
 RELAY_SIGNATURES = [
