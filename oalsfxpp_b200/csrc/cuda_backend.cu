@@ -351,6 +351,12 @@ public:
 				static_cast<size_t>(args.relay_smem_floats) * sizeof(float), st>>>(args); break;
 			OALSFX_RELAY_TABLE(OALSFX_RX)
 #undef OALSFX_RX
+#define OALSFX_MX(id, CT, F0, F1, F2, F3, duo_id) \
+		case id: \
+			prefer_shared(id, duo::duo_multi_kernel<CT, F0, F1, F2, F3>, 50); \
+			duo::duo_multi_kernel<CT, F0, F1, F2, F3><<<static_cast<unsigned>(args.tile_count), 64, tune_dyn_smem_, st>>>(args); break;
+			OALSFX_MULTI_TABLE(OALSFX_MX)
+#undef OALSFX_MX
 #define OALSFX_SX(id, CT) \
 		case id: \
 			if (!carveout_done_[id]) { \

@@ -90,12 +90,7 @@ __device__ __forceinline__ void store_passthrough_history(uint32_t* ss, int send
 }
 
 template <int CT, class F0, class F1, class F2, class F3>
-#ifdef OALSFX_DUO_MAXNREG
-__global__ void __maxnreg__(OALSFX_DUO_MAXNREG) duo_kernel(
-#else
-__global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(
-#endif
-	const __grid_constant__ MixArgs a)
+__device__ __forceinline__ void duo_body(const MixArgs& a)
 {
 	// A reverb in slot 3 is split: its input stage (B->A conversion, shelf filters, main-line feed,
 	// ~110 instructions per sample) runs in the front warp, which balances the two warps (500 / 413).
@@ -312,6 +307,50 @@ __global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(
 			store_passthrough_history<CT>(ss, 1 + a.aux_index[3], src, a, io_ok);
 		}
 	}
+}
+
+// One parameter class for the whole launch: the coefficient blocks are kernel arguments (constant bank).
+template <int CT, class F0, class F1, class F2, class F3>
+#ifdef OALSFX_DUO_MAXNREG
+__global__ void __maxnreg__(OALSFX_DUO_MAXNREG) duo_kernel(
+#else
+__global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(
+#endif
+	const __grid_constant__ MixArgs a)
+{
+	duo_body<CT, F0, F1, F2, F3>(a);
+}
+
+// One parameter class PER TILE (every stream block of 32 its own presets): the launch-wide part of the arguments
+// comes from the kernel arguments, the tile's coefficient blocks (direct / aux sends, four slots) and its pending-
+// update bits from a class table in HBM (MixArgs::class_table, indexed by tile_class[tile]); both are assembled
+// in shared memory and the same body runs from there.  Coefficients then cost a shared-memory load instead of
+// being constant-bank operands -- but the tile still runs the fused, prefetching pipeline in one launch for all
+// classes, where the alternatives are one launch per class or per-lane coefficient fetches (table mode).
+template <int CT, class F0, class F1, class F2, class F3>
+__global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_multi_kernel(const __grid_constant__ MixArgs a)
+{
+	__shared__ __align__(16) MixArgs sa;
+	const int tile = a.tiles ? static_cast<int>(a.tiles[blockIdx.x].tile) : a.tile_first + static_cast<int>(blockIdx.x);
+	const MixClassEntry* entry = a.class_table + a.tile_class[tile];
+	const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
+	uint32_t* ps = reinterpret_cast<uint32_t*>(&sa);
+	constexpr int kWords = static_cast<int>(sizeof(MixArgs) / 4), kCoef0 = static_cast<int>(kMixCoefOffset / 4),
+		kCoefWords = static_cast<int>(kMixCoefBytes / 4);
+	for (int i = threadIdx.x; i < kWords; i += 64) {
+		if (i < kCoef0 || i >= kCoef0 + kCoefWords) {
+			ps[i] = pa[i];
+		}
+	}
+	for (int i = threadIdx.x; i < kCoefWords; i += 64) {
+		ps[kCoef0 + i] = entry->coefs[i];
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		sa.update_mask = a.update_mask & entry->pending; // a.update_mask: all ones on the first block of a mix call
+	}
+	__syncthreads();
+	duo_body<CT, F0, F1, F2, F3>(sa);
 }
 
 } // namespace duo

@@ -65,6 +65,7 @@ struct Group {
 	bool identity = false;     // covers tiles 0..T-1 with all lanes
 	bool full_tiles = false;   // every listed tile takes part with all of its (existing) lanes
 	bool table = false;        // table mode: key.fx[] holds effect KINDS, streams differ in parameters
+	bool multi = false;        // class-per-tile launch: every tile has ONE parameter class, coefficient blocks per tile from HBM
 	size_t tile_begin = 0;     // into the concatenated tile list
 	int tile_count = 0;
 };
@@ -109,6 +110,13 @@ struct oalsfx_engine {
 	int32_t* lane_send_dev = nullptr;
 
 	std::vector<Group> groups;
+	// Class-per-tile launch (duo_multi_kernel): the class table and every tile's class index in HBM; `groups` is
+	// then the single multi group and `fallback_groups` holds the per-class / table-mode groups for the blocks the
+	// fused kernel cannot take (frames < 2).
+	std::vector<Group> fallback_groups;
+	MixClassEntry* class_table_dev = nullptr;
+	size_t class_table_cap = 0;
+	int32_t* tile_class_dev = nullptr;
 	bool groups_dirty = true;
 	long long launches = 0;
 	// Which fused kernel family serves whole-tile groups: 2 = automatic (default): the two-stage duo kernel,
@@ -138,6 +146,8 @@ struct oalsfx_engine {
 		}
 		be->release(send_state);
 		be->release(tile_list);
+		be->release(class_table_dev);
+		be->release(tile_class_dev);
 		be->release(slot_table_dev);
 		be->release(send_table_dev);
 		be->release(lane_send_dev);
@@ -439,6 +449,7 @@ struct oalsfx_engine {
 			g.identity = true;
 			g.tile_count = tiles;
 			groups.push_back(g);
+			fallback_groups.clear();
 			groups_dirty = false;
 			return true;
 		}
@@ -451,6 +462,7 @@ struct oalsfx_engine {
 			}
 			v.back().mask |= 1U << (s % kLanes);
 		}
+		const std::map<GroupKey, std::vector<TileRef>> full_keys = by_key;
 		// One launch per parameter class is fine for a handful of classes (each runs the fused kernels with
 		// constant-bank coefficients).  Beyond that the launches multiply -- every class touches most tiles --
 		// so the streams are grouped by effect KINDS only and the kTab* kernels fetch each stream's own
@@ -504,7 +516,84 @@ struct oalsfx_engine {
 		if (!be->upload(tile_list, all.data(), all.size() * sizeof(TileRef), nullptr) || !be->sync(nullptr)) {
 			return false;
 		}
+		if (!build_multi(full_keys)) {
+			return false;
+		}
 		groups_dirty = false;
+		return true;
+	}
+
+	// Class-per-tile launch: possible when every tile holds ONE parameter class (presets assigned in runs of 32
+	// streams), the signature has a duo_multi kernel and nothing needs the exact kernels.  One launch then covers
+	// all classes at the fused kernel's speed.
+	bool build_multi(const std::map<GroupKey, std::vector<TileRef>>& by_key)
+	{
+		fallback_groups.clear();
+		constexpr size_t kMultiMinGroups = 3; // one or two big classes: a constant-bank launch each is faster
+		if (by_key.size() < kMultiMinGroups || !be->has_relay() || channels != 2 || (family != 2 && family != 4)) {
+			return true;
+		}
+		std::vector<int32_t> tile_class(static_cast<size_t>(tiles), -1);
+		std::vector<MixClassEntry> table;
+		table.reserve(by_key.size());
+		uint32_t pending_any = 0;
+		const KernelInfo* infos = kernel_infos();
+		for (const auto& kv : by_key) {
+			const GroupKey& key = kv.first;
+			const SendClass& sc = send_classes[static_cast<size_t>(key.send)];
+			bool ok = sc.direct_coef.filter_type == 0;
+			int kinds[kMaxSlots];
+			for (int s = 0; s < kMaxSlots; ++s) {
+				const FxClass& fc = classes[static_cast<size_t>(key.fx[s])];
+				kinds[s] = kind_of_type(fc.type);
+				ok = ok && (kinds[s] == kKindNull || sc.aux_coef[s].filter_type == 0) && !(fc.coef.flags & kCoefUnstable);
+			}
+			ok = ok && std::memcmp(infos[kChainStereo].kind, kinds, sizeof(kinds)) == 0;
+			for (const TileRef& t : kv.second) {
+				const int lanes_here = std::min(kLanes, streams - static_cast<int>(t.tile) * kLanes);
+				const uint32_t want = (lanes_here == kLanes ? 0xFFFFFFFFU : ((1U << lanes_here) - 1U));
+				ok = ok && t.mask == want;
+				tile_class[t.tile] = static_cast<int32_t>(table.size());
+			}
+			if (!ok) {
+				return true;
+			}
+			Group g;
+			g.key = key;
+			MixArgs a;
+			fill_common(a, g, 2, nullptr, nullptr, OALSFX_LAYOUT_STREAM_MAJOR, 2, 0);
+			for (int s = 0; s < kMaxSlots; ++s) {
+				fill_slot(a, g, s, s, false);
+			}
+			sanitize_gains(a);
+			MixClassEntry e;
+			std::memset(&e, 0, sizeof(e));
+			e.pending = key.pending;
+			std::memcpy(e.coefs, reinterpret_cast<const char*>(&a) + kMixCoefOffset, kMixCoefBytes);
+			table.push_back(e);
+			pending_any |= key.pending;
+		}
+		if (!grow(class_table_dev, class_table_cap, table.size())) {
+			return false;
+		}
+		if (!tile_class_dev) {
+			tile_class_dev = static_cast<int32_t*>(dev_alloc(static_cast<size_t>(tiles) * sizeof(int32_t)));
+			if (!tile_class_dev) {
+				return false;
+			}
+		}
+		if (!be->upload(class_table_dev, table.data(), table.size() * sizeof(MixClassEntry), nullptr) ||
+			!be->upload(tile_class_dev, tile_class.data(), tile_class.size() * sizeof(int32_t), nullptr) || !be->sync(nullptr)) {
+			return false;
+		}
+		fallback_groups.swap(groups);
+		Group g;
+		g.key = by_key.begin()->first;
+		g.key.pending = pending_any;
+		g.identity = true;
+		g.multi = true;
+		g.tile_count = tiles;
+		groups.assign(1, g);
 		return true;
 	}
 
@@ -598,6 +687,19 @@ struct oalsfx_engine {
 	bool launch_group(const Group& g, int frames, const float* src, float* dst, int layout,
 		long long frames_total, long long frame0, bool first_block, void* stream)
 	{
+		if (g.multi) {
+			MixArgs a;
+			fill_common(a, g, frames, src, dst, layout, frames_total, frame0);
+			a.with_dry = 1;
+			for (int s = 0; s < kMaxSlots; ++s) {
+				fill_slot(a, g, s, s, false); // pointers and strides; the coefficient blocks come from the class table
+			}
+			a.update_mask = first_block ? 0xFFFFFFFFU : 0U;
+			a.class_table = class_table_dev;
+			a.tile_class = tile_class_dev;
+			++launches;
+			return be->launch_mix(kMultiChainStereo, a, stream);
+		}
 		if (g.table) {
 			// key.fx[] holds the kinds; one exact single-effect pass per slot, coefficients from the tables
 			bool first = true;
@@ -983,7 +1085,7 @@ int oalsfx_engine_mix(oalsfx_engine* e, int frames, const float* src, float* dst
 			max_slices = std::max(2, std::atoi(tune));
 		}
 		const int slices = std::min(e->tiles / 64, max_slices);
-		if (frames <= kMaxBlockFrames && e->groups.size() == 1 && e->groups[0].identity && slices >= 2 &&
+		if (frames <= kMaxBlockFrames && e->groups.size() == 1 && e->groups[0].identity && (!e->groups[0].multi || frames >= 2) && slices >= 2 &&
 			layout == OALSFX_LAYOUT_STREAM_MAJOR) {
 			if (!e->pipe_in) {
 				e->pipe_in = e->be->stream_create();
@@ -1036,7 +1138,9 @@ int oalsfx_engine_mix(oalsfx_engine* e, int frames, const float* src, float* dst
 			return e->fail(OALSFX_ERR_DEVICE, "Group table upload failed: " + e->be->error());
 		}
 		bool had_pending = false;
-		for (const Group& g : e->groups) {
+		const bool use_fallback = e->groups.size() == 1 && e->groups[0].multi && todo < 2;
+		had_pending = use_fallback && e->groups[0].key.pending != 0;
+		for (const Group& g : (use_fallback ? e->fallback_groups : e->groups)) {
 			had_pending = had_pending || g.key.pending != 0;
 			if (!e->launch_group(g, todo, dsrc, ddst, layout, frames, done, first_block, cuda_stream)) {
 				return e->fail(OALSFX_ERR_DEVICE, e->be->error());

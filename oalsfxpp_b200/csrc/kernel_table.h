@@ -48,6 +48,10 @@
 #define OALSFX_DUO_TABLE(DX) \
 	DX(kDuoChainStereo, 2, FxEqualizer, FxModDelay, FxEcho, FxReverb, kChainStereo)
 
+// Class-per-tile duo kernels (duo_multi_kernel): MX(id, CT, F0, F1, F2, F3, duo id with the same signature).
+#define OALSFX_MULTI_TABLE(MX) \
+	MX(kMultiChainStereo, 2, FxEqualizer, FxModDelay, FxEcho, FxReverb, kDuoChainStereo)
+
 // Quartet kernels (quartet.cuh: four pipeline stages per tile -- dry + slot 0 | slots 1, 2 + reverb input |
 // reverb early half | reverb late half + output).  TX(id, CT, F0, F1, F2, F3, twin), same twin rule.
 #define OALSFX_QUARTET_TABLE(TX) \
@@ -108,6 +112,9 @@ enum KernelId : int {
 #define OALSFX_SX(id, CT) id,
 	OALSFX_SPAN_TABLE(OALSFX_SX)
 #undef OALSFX_SX
+#define OALSFX_MX(id, CT, F0, F1, F2, F3, duo) id,
+	OALSFX_MULTI_TABLE(OALSFX_MX)
+#undef OALSFX_MX
 	kKernelEnd
 };
 
@@ -229,6 +236,9 @@ inline const char* kernel_name(int id)
 #define OALSFX_SX(sid, CT) if (id == sid) return #sid;
 	OALSFX_SPAN_TABLE(OALSFX_SX)
 #undef OALSFX_SX
+#define OALSFX_MX(mid, CT, F0, F1, F2, F3, duo) if (id == mid) return #mid;
+	OALSFX_MULTI_TABLE(OALSFX_MX)
+#undef OALSFX_MX
 	return "?";
 }
 

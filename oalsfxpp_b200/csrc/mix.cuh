@@ -10,6 +10,7 @@
 #ifndef OALSFX_MIX_CUH
 #define OALSFX_MIX_CUH
 
+#include <cstddef>
 #include <type_traits>
 
 #include "fx.cuh"
@@ -65,6 +66,19 @@ struct MixArgs {
 	int32_t relay_smem_floats;        // dynamic shared memory of the launch
 	// Span kernels (span.cuh): frames per block-parallel span (host-checked against every delay of slot[0])
 	int32_t span_frames;
+	// Class-per-tile kernels (duo_multi_kernel): tile t runs with class_table[tile_class[t]]
+	const struct MixClassEntry* class_table;
+	const int32_t* tile_class;
+};
+
+// The per-class part of MixArgs: direct, aux[], slot[] (contiguous), plus the class's pending-update bits.
+constexpr size_t kMixCoefOffset = offsetof(MixArgs, direct);
+constexpr size_t kMixCoefBytes = offsetof(MixArgs, slot_table) - offsetof(MixArgs, direct);
+static_assert(kMixCoefOffset % 4 == 0 && kMixCoefBytes % 4 == 0 && sizeof(MixArgs) % 4 == 0, "word copies");
+struct MixClassEntry {
+	uint32_t pending;
+	uint32_t reserved[3];
+	uint32_t coefs[kMixCoefBytes / 4];
 };
 
 // Send shelf filters (reference: apply_filters, oalsfxpp.cpp:3101-3143).  Pass-through still

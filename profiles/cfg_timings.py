@@ -62,6 +62,9 @@ def cfg2_schedule(eng, b):
     eng.set_effect(0, T.equalizer, eq)
 
 
+TABLE_CHUNK = [0]  # streams per run of one preset (0: n / 904, i.e. mixed tiles)
+
+
 def all_presets(eng):
     """Slot 3: stream s gets reverb preset s mod 113 -- 113 parameter classes in one engine (table mode)."""
     names = ox.reverb_preset_names()
@@ -70,7 +73,7 @@ def all_presets(eng):
         # streams i, i + 113, ... : set in strided runs of one stream is slow from Python; use blocks of streams instead
         pass
     n = eng.num_streams
-    chunk = max(1, n // (len(per) * 8))
+    chunk = TABLE_CHUNK[0] or max(1, n // (len(per) * 8))
     s = 0
     k = 0
     while s < n:
@@ -100,6 +103,12 @@ def main():
         run("table mode: cfg4 chain, 113 reverb presets over 16384 stereo streams", 16384, F.stereo, 48000,
             [T.equalizer, T.chorus, T.echo, T.eax_reverb], 236, blocks=10, warm=3, setup=all_presets),
     ]
+    # the same with every run of 32 streams (one tile) its own preset: ONE class-per-tile launch (duo_multi_kernel)
+    TABLE_CHUNK[0] = 32
+    out.append(run("class per tile: cfg4 chain, 113 reverb presets in runs of 32 over 16384 stereo streams", 16384, F.stereo, 48000,
+                   [T.equalizer, T.chorus, T.echo, T.eax_reverb], 236, blocks=10, warm=3, setup=all_presets))
+    out.append(run("class per tile: cfg4 chain, 113 reverb presets in runs of 32 over 65536 stereo streams", 65536, F.stereo, 48000,
+                   [T.equalizer, T.chorus, T.echo, T.eax_reverb], 236, blocks=10, warm=3, setup=all_presets))
     print(json.dumps({"gpu": torch.cuda.get_device_name(0), "block_frames": BLOCK, "results": out}, indent=1))
 
 

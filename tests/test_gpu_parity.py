@@ -487,6 +487,60 @@ def test_many_parameter_sets_table_mode(checker):
     assert launches <= nblocks * 2 * 4
 
 
+def test_class_per_tile_launch_many_presets(checker):
+    """Every run of 32 streams its own reverb preset / equalizer / echo settings (40 parameter classes, a ragged last
+    tile): ONE duo_multi launch per block with per-tile coefficient blocks from HBM.  A preset change on some tiles
+    in block 2 (pending bits per class), a 1-frame block (the fused kernel needs >= 2 frames: per-class fallback)."""
+    lib = _lib()
+    names = ox.reverb_preset_names(lib=lib)
+    tiles = 40
+    S = tiles * 32 - 5
+    blocks = [1024, 500, 1024, 1, 777]
+    total = sum(blocks)
+    x = np.stack([H.noise(3000 + s, 2, total) for s in range(S)])
+    y = np.empty_like(x)
+
+    def config(t, phase):
+        g, n = names[(7 * t + 3 + 11 * phase * (t % 3 == 0)) % len(names)]
+        return [(T.equalizer, ox.default_props(T.equalizer, lib=lib, mid1_gain_=0.6 + 0.03 * t)),
+                (T.chorus, ox.default_props(T.chorus, lib=lib, depth_=0.05 + 0.002 * t)),
+                (T.echo, ox.default_props(T.echo, lib=lib, delay_=0.03 + 0.002 * t, feedback_=0.2 + 0.01 * (t % 30))),
+                (T.eax_reverb, ox.reverb_preset(g, n, lib=lib))]
+
+    with ox.Engine(S, F.stereo, 48000, 4, lib=lib) as eng:
+        for t in range(tiles):
+            n = min(32, S - 32 * t)
+            for slot, (et, p) in enumerate(config(t, 0)):
+                eng.set_effect(slot, et, p, first_stream=32 * t, n_streams=n)
+        at = 0
+        counts = []
+        for b, n in enumerate(blocks):
+            if b == 2:
+                for t in range(0, tiles, 3):
+                    m = min(32, S - 32 * t)
+                    for slot, (et, p) in enumerate(config(t, 1)):
+                        eng.set_effect(slot, et, p, first_stream=32 * t, n_streams=m)
+            before = eng.launch_count
+            y[:, at:at + n] = eng.mix(np.ascontiguousarray(x[:, at:at + n]))
+            counts.append(eng.launch_count - before)
+            at += n
+    assert [c for c, n in zip(counts, blocks) if n >= 2] == [1, 1, 1, 1], counts
+    for s in (0, 31, 32, 95, 96, 100, 640, 1000, S - 1):
+        t = s // 32
+        script = []
+        for slot, (et, p) in enumerate(config(t, 0)):
+            script += [("type", slot, et), ("props", slot, p)]
+        script += [("apply",)]
+        for b, n in enumerate(blocks):
+            if b == 2 and t % 3 == 0:
+                for slot, (et, p) in enumerate(config(t, 1)):
+                    script += [("type", slot, et), ("props", slot, p)]
+                script += [("apply",)]
+            script += [("mix", n)]
+        expect = H.run_script_orc(checker, F.stereo, 48000, 4, script, x[s])
+        _assert_match(expect, y[s], True, f"class-per-tile stream {s}")
+
+
 def test_stream_major_bus_reduce_is_exact_enough_and_deterministic():
     """The coalesced two-pass reduction (row groups of 128 streams, then the groups): equals the float64 sum
     of the per-stream outputs within 1e-5 * sqrt(S) and is bit-identical from call to call."""
