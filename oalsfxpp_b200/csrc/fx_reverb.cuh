@@ -143,6 +143,7 @@ struct FxReverbT {
 	bool primed, can_pf;
 	int32_t pf_row4;   // window row of the first position of the batch holding the current position
 	bool pan_static;   // this sub-chunk: no gain ramps and every one of the 8 x C pan gains is audible
+	uint32_t direct_groups; // this sub-chunk: tap groups (bit = OLD-tap group id) the window cannot serve, read in place
 
 	unsigned pf_s;     // shared-space address of the warp's window (lane offset removed), device build
 	OALSFX_HD void set_prefetch(float* column)
@@ -253,17 +254,23 @@ struct FxReverbT {
 		// Reading kPfDepth samples ahead is legal when nothing written during those samples can be what
 		// the prefetch reads: every delay > kPfDepth, the late taps that far beyond the late feed write,
 		// no cross-fade (reads both tap sets), no modulation (the late line read position moves).
-		bool ok = pf_col != nullptr && !faded && (!LATE || (c.mod_depth == 0.0F && mod_filter == 0.0F));
+		// A tap group that breaks the rule (a zero reflections / late delay, the modulated late line of the "underwater"
+		// kind of preset) is read in place instead, the other groups keep the window ("mixed" body).
+		const bool ok = pf_col != nullptr && !faded;
+		uint32_t direct = (LATE && !(c.mod_depth == 0.0F && mod_filter == 0.0F)) ? (1U << 5) : 0U;
 		OALSFX_UNROLL
 		for (int l = 0; l < 4; ++l) {
 			if (EARLY) {
-				ok = ok && c.early_tap[l] > kPfDepth && c.early_ap_off[l] > kPfDepth && c.early_off[l] > kPfDepth;
+				direct |= (c.early_tap[l] > kPfDepth ? 0U : 1U << 0) | (c.early_ap_off[l] > kPfDepth ? 0U : 1U << 1) |
+					(c.early_off[l] > kPfDepth ? 0U : 1U << 2);
 			}
 			if (LATE) {
-				ok = ok && c.late_tap[l] > c.late_feed_tap + kPfDepth && c.late_ap_off[l] > kPfDepth && c.late_off[l] > kPfDepth;
+				direct |= (c.late_tap[l] > c.late_feed_tap + kPfDepth ? 0U : 1U << 3) | (c.late_ap_off[l] > kPfDepth ? 0U : 1U << 4) |
+					(c.late_off[l] > kPfDepth ? 0U : 1U << 5);
 			}
 		}
 		can_pf = ok;
+		direct_groups = direct;
 		pan_static = true;
 		const int counter = block_frames - base;
 		const float delta = 1.0F / static_cast<float>(counter);
@@ -340,13 +347,13 @@ struct FxReverbT {
 	}
 
 	// Delay read (oalsfxpp.cpp:7358-7406): prefetched value, direct read, or old/new cross-fade.
-	template <bool PF>
-	OALSFX_HD float tap(int tap_index, int ring_word0, int mask, int pos, int group, int line, int new_d, float mu) const
+	template <bool PF, bool MIXED = false>
+	OALSFX_HD float tap(int tap_index, int ring_word0, int mask, int pos, int group, int line, int new_d, float mu, uint32_t dg = 0) const
 	{
-		if (PF) {
+		if (PF && (!MIXED || ((dg >> group) & 1U) == 0)) {
 			return pf_cur[(tap_index - kTap0) * kLanes];
 		}
-		if (!faded) {
+		if (PF || !faded) {
 			return ring.ld(ring_word0 + ((pos - new_d) & mask)); // committed: old == new
 		}
 		const float a = ring.ld(ring_word0 + ((pos - old_tap(group, line)) & mask));
@@ -379,17 +386,17 @@ struct FxReverbT {
 	}
 
 	// vector_allpass_x (oalsfxpp.cpp:7533-7562) on line pairs.
-	template <bool PF>
+	template <bool PF, bool MIXED = false>
 	OALSFX_HD void vector_allpass2(const ReverbCoef& c, F2& va, F2& vb, int ring_idx, int tap_base, int group,
-		const int32_t* new_off, int pos, float mu) const
+		const int32_t* new_off, int pos, float mu, uint32_t dg = 0) const
 	{
 		const int len = c.mask[ring_idx] + 1;
 		const int word0 = c.ring_base[ring_idx];
 		const int mask = c.mask[ring_idx];
-		const F2 ta = f2(tap<PF>(tap_base + 0, word0 + 0 * len, mask, pos, group, 0, new_off[0], mu),
-			tap<PF>(tap_base + 1, word0 + 1 * len, mask, pos, group, 1, new_off[1], mu));
-		const F2 tb = f2(tap<PF>(tap_base + 2, word0 + 2 * len, mask, pos, group, 2, new_off[2], mu),
-			tap<PF>(tap_base + 3, word0 + 3 * len, mask, pos, group, 3, new_off[3], mu));
+		const F2 ta = f2(tap<PF, MIXED>(tap_base + 0, word0 + 0 * len, mask, pos, group, 0, new_off[0], mu, dg),
+			tap<PF, MIXED>(tap_base + 1, word0 + 1 * len, mask, pos, group, 1, new_off[1], mu, dg));
+		const F2 tb = f2(tap<PF, MIXED>(tap_base + 2, word0 + 2 * len, mask, pos, group, 2, new_off[2], mu, dg),
+			tap<PF, MIXED>(tap_base + 3, word0 + 3 * len, mask, pos, group, 3, new_off[3], mu, dg));
 		const F2 ina = va, inb = vb;
 		va = ta - (ina * c.ap_feed_coeff);
 		vb = tb - (inb * c.ap_feed_coeff);
@@ -445,7 +452,10 @@ struct FxReverbT {
 #if defined(__CUDA_ARCH__)
 		// The batched copies are a whole-warp affair (a lane fetches other lanes' streams), so the
 		// decision is a vote: every lane of the tile must be in the prefetchable state.
-		if (OALSFX_LIKELY(pf_col != nullptr && __all_sync(0xFFFFFFFFU, can_pf))) {
+		const bool window_all = pf_col != nullptr && __all_sync(0xFFFFFFFFU, can_pf && direct_groups == 0);
+		// (second vote only off the steady state) some lane needs a tap group read in place: the union of the groups
+		const bool window_some = !window_all && pf_col != nullptr && __all_sync(0xFFFFFFFFU, can_pf);
+		if (OALSFX_LIKELY(window_all || window_some)) {
 			// Invariant while primed, at position r of the batch whose first position sits in window row
 			// pf_row4: that batch has landed, and the next one has been requested iff r >= kPfIssueAt.
 			const int r = pos & (kPfBatch - 1);
@@ -484,7 +494,11 @@ struct FxReverbT {
 			int row = pf_row4 + r;
 			row = (row >= kPfSlots ? row - kPfSlots : row);
 			pf_cur = pf_col + row * (kTaps * kLanes);
-			body<CT, true>(c, wet, acc, channels, pos); // branch-free: every read is a shared-memory load
+			if (OALSFX_LIKELY(window_all)) {
+				body<CT, true>(c, wet, acc, channels, pos); // branch-free: every read is a shared-memory load
+			} else {
+				body<CT, true, true>(c, wet, acc, channels, pos, __reduce_or_sync(0xFFFFFFFFU, direct_groups));
+			}
 		} else {
 			if (primed) {
 				// leaving the batched mode: nothing of the window may still be in flight when it is primed
@@ -504,8 +518,8 @@ struct FxReverbT {
 	}
 
 	// One sample.  PF: all 24 ring reads come from the prefetch window (steady state).
-	template <int CT, bool PF>
-	OALSFX_HD void body(const ReverbCoef& c, const float* wet, float* acc, int channels, const int pos)
+	template <int CT, bool PF, bool MIXED = false>
+	OALSFX_HD void body(const ReverbCoef& c, const float* wet, float* acc, int channels, const int pos, const uint32_t dg = 0)
 	{
 		const float mu = fade;
 
@@ -523,20 +537,20 @@ struct FxReverbT {
 
 		if (EARLY) {
 		// ---- early reflections (oalsfxpp.cpp:7625-7672) ----
-		fa = f2(tap<PF>(0, main0 + 0 * main_len, main_mask, pos, 0, 0, c.early_tap[0], mu),
-			tap<PF>(1, main0 + 1 * main_len, main_mask, pos, 0, 1, c.early_tap[1], mu)) * f2(c.early_tap_coeff[0], c.early_tap_coeff[1]);
-		fb = f2(tap<PF>(2, main0 + 2 * main_len, main_mask, pos, 0, 2, c.early_tap[2], mu),
-			tap<PF>(3, main0 + 3 * main_len, main_mask, pos, 0, 3, c.early_tap[3], mu)) * f2(c.early_tap_coeff[2], c.early_tap_coeff[3]);
-		vector_allpass2<PF>(c, fa, fb, 1, 4, 1, c.early_ap_off, pos, mu);
+		fa = f2(tap<PF, MIXED>(0, main0 + 0 * main_len, main_mask, pos, 0, 0, c.early_tap[0], mu, dg),
+			tap<PF, MIXED>(1, main0 + 1 * main_len, main_mask, pos, 0, 1, c.early_tap[1], mu, dg)) * f2(c.early_tap_coeff[0], c.early_tap_coeff[1]);
+		fb = f2(tap<PF, MIXED>(2, main0 + 2 * main_len, main_mask, pos, 0, 2, c.early_tap[2], mu, dg),
+			tap<PF, MIXED>(3, main0 + 3 * main_len, main_mask, pos, 0, 3, c.early_tap[3], mu, dg)) * f2(c.early_tap_coeff[2], c.early_tap_coeff[3]);
+		vector_allpass2<PF, MIXED>(c, fa, fb, 1, 4, 1, c.early_ap_off, pos, mu, dg);
 		// delay_line_in4_rev: line j receives f[3 - j]
 		ring.st(eline0 + 0 * eline_len + (pos & eline_mask), f2_hi(fb));
 		ring.st(eline0 + 1 * eline_len + (pos & eline_mask), f2_lo(fb));
 		ring.st(eline0 + 2 * eline_len + (pos & eline_mask), f2_hi(fa));
 		ring.st(eline0 + 3 * eline_len + (pos & eline_mask), f2_lo(fa));
-		fa = fa + (f2(tap<PF>(8, eline0 + 0 * eline_len, eline_mask, pos, 2, 0, c.early_off[0], mu),
-			tap<PF>(9, eline0 + 1 * eline_len, eline_mask, pos, 2, 1, c.early_off[1], mu)) * f2(c.early_coeff[0], c.early_coeff[1]));
-		fb = fb + (f2(tap<PF>(10, eline0 + 2 * eline_len, eline_mask, pos, 2, 2, c.early_off[2], mu),
-			tap<PF>(11, eline0 + 3 * eline_len, eline_mask, pos, 2, 3, c.early_off[3], mu)) * f2(c.early_coeff[2], c.early_coeff[3]));
+		fa = fa + (f2(tap<PF, MIXED>(8, eline0 + 0 * eline_len, eline_mask, pos, 2, 0, c.early_off[0], mu, dg),
+			tap<PF, MIXED>(9, eline0 + 1 * eline_len, eline_mask, pos, 2, 1, c.early_off[1], mu, dg)) * f2(c.early_coeff[0], c.early_coeff[1]));
+		fb = fb + (f2(tap<PF, MIXED>(10, eline0 + 2 * eline_len, eline_mask, pos, 2, 2, c.early_off[2], mu, dg),
+			tap<PF, MIXED>(11, eline0 + 3 * eline_len, eline_mask, pos, 2, 3, c.early_off[3], mu, dg)) * f2(c.early_coeff[2], c.early_coeff[3]));
 		early_out[0] = f2_lo(fa);
 		early_out[1] = f2_hi(fa);
 		early_out[2] = f2_lo(fb);
@@ -558,7 +572,7 @@ struct FxReverbT {
 		// calc_modulation_delays (oalsfxpp.cpp:7443-7470); when depth and filter are both zero the
 		// product range*sinus is +-0 and the delay is 0 whatever the sinus is.
 		int mod_delay = 0;
-		if (PF) { // can_pf implies depth == 0 and filter == 0: the delay is 0, only the index moves
+		if (PF && !MIXED) { // every group served by the window implies depth == 0 and filter == 0: the delay is 0, only the index moves
 			mod_index += 1;
 			if (mod_index >= mod_range) {
 				mod_index = 0;
@@ -575,15 +589,15 @@ struct FxReverbT {
 				mod_delay = static_cast<int>(lroundf(mod_filter * sinus));
 			}
 		}
-		fa = f2(tap<PF>(12, main0 + 0 * main_len, main_mask, pos, 3, 0, c.late_tap[0], mu),
-			tap<PF>(13, main0 + 1 * main_len, main_mask, pos, 3, 1, c.late_tap[1], mu)) * c.density_gain;
-		fb = f2(tap<PF>(14, main0 + 2 * main_len, main_mask, pos, 3, 2, c.late_tap[2], mu),
-			tap<PF>(15, main0 + 3 * main_len, main_mask, pos, 3, 3, c.late_tap[3], mu)) * c.density_gain;
+		fa = f2(tap<PF, MIXED>(12, main0 + 0 * main_len, main_mask, pos, 3, 0, c.late_tap[0], mu, dg),
+			tap<PF, MIXED>(13, main0 + 1 * main_len, main_mask, pos, 3, 1, c.late_tap[1], mu, dg)) * c.density_gain;
+		fb = f2(tap<PF, MIXED>(14, main0 + 2 * main_len, main_mask, pos, 3, 2, c.late_tap[2], mu, dg),
+			tap<PF, MIXED>(15, main0 + 3 * main_len, main_mask, pos, 3, 3, c.late_tap[3], mu, dg)) * c.density_gain;
 		const int mod_pos = pos - mod_delay;
-		fa = fa + f2(tap<PF>(16, lline0 + 0 * lline_len, lline_mask, mod_pos, 5, 0, c.late_off[0], mu),
-			tap<PF>(17, lline0 + 1 * lline_len, lline_mask, mod_pos, 5, 1, c.late_off[1], mu));
-		fb = fb + f2(tap<PF>(18, lline0 + 2 * lline_len, lline_mask, mod_pos, 5, 2, c.late_off[2], mu),
-			tap<PF>(19, lline0 + 3 * lline_len, lline_mask, mod_pos, 5, 3, c.late_off[3], mu));
+		fa = fa + f2(tap<PF, MIXED>(16, lline0 + 0 * lline_len, lline_mask, mod_pos, 5, 0, c.late_off[0], mu, dg),
+			tap<PF, MIXED>(17, lline0 + 1 * lline_len, lline_mask, mod_pos, 5, 1, c.late_off[1], mu, dg));
+		fb = fb + f2(tap<PF, MIXED>(18, lline0 + 2 * lline_len, lline_mask, mod_pos, 5, 2, c.late_off[2], mu, dg),
+			tap<PF, MIXED>(19, lline0 + 3 * lline_len, lline_mask, mod_pos, 5, 3, c.late_off[3], mu, dg));
 		OALSFX_UNROLL
 		for (int h = 0; h < 2; ++h) {
 			// late_t60_filter: two first-order sections and the mid gain (oalsfxpp.cpp:7691-7719), lines 2h, 2h+1
@@ -604,7 +618,7 @@ struct FxReverbT {
 				fb = out;
 			}
 		}
-		vector_allpass2<PF>(c, fa, fb, 3, 20, 4, c.late_ap_off, pos, mu);
+		vector_allpass2<PF, MIXED>(c, fa, fb, 3, 20, 4, c.late_ap_off, pos, mu, dg);
 		late_out[0] = f2_lo(fa);
 		late_out[1] = f2_hi(fa);
 		late_out[2] = f2_lo(fb);
