@@ -351,6 +351,13 @@ public:
 				static_cast<size_t>(args.relay_smem_floats) * sizeof(float), st>>>(args); break;
 			OALSFX_RELAY_TABLE(OALSFX_RX)
 #undef OALSFX_RX
+#define OALSFX_RX(id, CT, HEAVY) \
+		case id: \
+			relay_attributes(id, relay::relay_multi_kernel<CT, HEAVY>); \
+			relay::relay_multi_kernel<CT, HEAVY><<<static_cast<unsigned>(args.tile_count), relay::kThreads, \
+				static_cast<size_t>(args.relay_smem_floats) * sizeof(float), st>>>(args); break;
+			OALSFX_RELAY_MULTI_TABLE(OALSFX_RX)
+#undef OALSFX_RX
 #define OALSFX_MX(id, CT, F0, F1, F2, F3, duo_id) \
 		case id: \
 			prefer_shared(id, duo::duo_multi_kernel<CT, F0, F1, F2, F3>, 50); \

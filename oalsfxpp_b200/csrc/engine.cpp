@@ -524,13 +524,17 @@ struct oalsfx_engine {
 	}
 
 	// Class-per-tile launch: possible when every tile holds ONE parameter class (presets assigned in runs of 32
-	// streams), the signature has a duo_multi kernel and nothing needs the exact kernels.  One launch then covers
-	// all classes at the fused kernel's speed.
+	// streams), all classes share one slot signature that has a *_multi kernel (the fused stereo chain, or the relay
+	// pipeline for anything else with one or two channels) and nothing needs the exact kernels.  One launch then
+	// covers all classes at the fused kernel's speed.
+	int multi_kernel = -1;
+	int multi_kinds[kMaxSlots] = {};   // per slot
 	bool build_multi(const std::map<GroupKey, std::vector<TileRef>>& by_key)
 	{
 		fallback_groups.clear();
+		multi_kernel = -1;
 		constexpr size_t kMultiMinGroups = 3; // one or two big classes: a constant-bank launch each is faster
-		if (by_key.size() < kMultiMinGroups || !be->has_relay() || channels != 2 || (family != 2 && family != 4)) {
+		if (by_key.size() < kMultiMinGroups || !be->has_relay() || (channels != 1 && channels != 2) || (family != 2 && family != 4)) {
 			return true;
 		}
 		std::vector<int32_t> tile_class(static_cast<size_t>(tiles), -1);
@@ -538,6 +542,8 @@ struct oalsfx_engine {
 		table.reserve(by_key.size());
 		uint32_t pending_any = 0;
 		const KernelInfo* infos = kernel_infos();
+		bool first = true, heavy = false, chain = false;
+		int active = 0;
 		for (const auto& kv : by_key) {
 			const GroupKey& key = kv.first;
 			const SendClass& sc = send_classes[static_cast<size_t>(key.send)];
@@ -548,7 +554,16 @@ struct oalsfx_engine {
 				kinds[s] = kind_of_type(fc.type);
 				ok = ok && (kinds[s] == kKindNull || sc.aux_coef[s].filter_type == 0) && !(fc.coef.flags & kCoefUnstable);
 			}
-			ok = ok && std::memcmp(infos[kChainStereo].kind, kinds, sizeof(kinds)) == 0;
+			if (first) {
+				std::memcpy(multi_kinds, kinds, sizeof(kinds));
+				chain = channels == 2 && std::memcmp(infos[kChainStereo].kind, kinds, sizeof(kinds)) == 0;
+				for (int s = 0; s < kMaxSlots; ++s) {
+					active += kinds[s] != kKindNull ? 1 : 0;
+					heavy = heavy || kinds[s] == kKindReverb;
+				}
+				first = false;
+			}
+			ok = ok && std::memcmp(multi_kinds, kinds, sizeof(kinds)) == 0 && active >= 1;
 			for (const TileRef& t : kv.second) {
 				const int lanes_here = std::min(kLanes, streams - static_cast<int>(t.tile) * kLanes);
 				const uint32_t want = (lanes_here == kLanes ? 0xFFFFFFFFU : ((1U << lanes_here) - 1U));
@@ -562,13 +577,17 @@ struct oalsfx_engine {
 			g.key = key;
 			MixArgs a;
 			fill_common(a, g, 2, nullptr, nullptr, OALSFX_LAYOUT_STREAM_MAJOR, 2, 0);
-			for (int s = 0; s < kMaxSlots; ++s) {
-				fill_slot(a, g, s, s, false);
-			}
-			sanitize_gains(a);
 			MixClassEntry e;
 			std::memset(&e, 0, sizeof(e));
-			e.pending = key.pending;
+			int pos = 0;
+			for (int s = 0; s < kMaxSlots; ++s) { // the chain kernel addresses slots by index, the relay by compacted position
+				if (chain || kinds[s] != kKindNull) {
+					fill_slot(a, g, pos, s, false);
+					e.pending |= ((key.pending >> s) & 1U) << pos;
+					++pos;
+				}
+			}
+			sanitize_gains(a);
 			std::memcpy(e.coefs, reinterpret_cast<const char*>(&a) + kMixCoefOffset, kMixCoefBytes);
 			table.push_back(e);
 			pending_any |= key.pending;
@@ -586,6 +605,8 @@ struct oalsfx_engine {
 			!be->upload(tile_class_dev, tile_class.data(), tile_class.size() * sizeof(int32_t), nullptr) || !be->sync(nullptr)) {
 			return false;
 		}
+		multi_kernel = chain ? kMultiChainStereo :
+			channels == 1 ? (heavy ? kRelayMultiMonoHeavy : kRelayMultiMono) : (heavy ? kRelayMultiStereoHeavy : kRelayMultiStereo);
 		fallback_groups.swap(groups);
 		Group g;
 		g.key = by_key.begin()->first;
@@ -691,14 +712,25 @@ struct oalsfx_engine {
 			MixArgs a;
 			fill_common(a, g, frames, src, dst, layout, frames_total, frame0);
 			a.with_dry = 1;
+			const bool chain = multi_kernel == kMultiChainStereo;
+			int pos = 0, floats = 0;
 			for (int s = 0; s < kMaxSlots; ++s) {
-				fill_slot(a, g, s, s, false); // pointers and strides; the coefficient blocks come from the class table
+				if (chain || multi_kinds[s] != kKindNull) {
+					fill_slot(a, g, pos, s, false); // pointers and strides; the coefficient blocks come from the class table
+					a.relay_kind[pos] = multi_kinds[s];
+					a.relay_win[pos] = floats;
+					floats += multi_kinds[s] == kKindReverb ? kPfWarpFloats :
+						(multi_kinds[s] == kKindModDelay || multi_kinds[s] == kKindEcho) ? kFwWarpFloats : 0;
+					++pos;
+				}
 			}
+			a.relay_count = pos;
+			a.relay_smem_floats = floats;
 			a.update_mask = first_block ? 0xFFFFFFFFU : 0U;
 			a.class_table = class_table_dev;
 			a.tile_class = tile_class_dev;
 			++launches;
-			return be->launch_mix(kMultiChainStereo, a, stream);
+			return be->launch_mix(multi_kernel, a, stream);
 		}
 		if (g.table) {
 			// key.fx[] holds the kinds; one exact single-effect pass per slot, coefficients from the tables

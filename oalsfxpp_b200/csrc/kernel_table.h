@@ -80,6 +80,12 @@
 	RX(kRelayStereo, 2, false) \
 	RX(kRelayMonoHeavy, 1, true) \
 	RX(kRelayStereoHeavy, 2, true)
+// the same with one parameter class per tile (relay_multi_kernel)
+#define OALSFX_RELAY_MULTI_TABLE(RX) \
+	RX(kRelayMultiMono, 1, false) \
+	RX(kRelayMultiStereo, 2, false) \
+	RX(kRelayMultiMonoHeavy, 1, true) \
+	RX(kRelayMultiStereoHeavy, 2, true)
 
 // Span kernels (span.cuh): the single-reverb-slot signature block-parallel in time.  SX(id, CT).
 #define OALSFX_SPAN_TABLE(SX) \
@@ -108,6 +114,7 @@ enum KernelId : int {
 #undef OALSFX_TBX
 #define OALSFX_RX(id, CT, HEAVY) id,
 	OALSFX_RELAY_TABLE(OALSFX_RX)
+	OALSFX_RELAY_MULTI_TABLE(OALSFX_RX)
 #undef OALSFX_RX
 #define OALSFX_SX(id, CT) id,
 	OALSFX_SPAN_TABLE(OALSFX_SX)
@@ -232,6 +239,7 @@ inline const char* kernel_name(int id)
 #undef OALSFX_TBX
 #define OALSFX_RX(rid, CT, HEAVY) if (id == rid) return #rid;
 	OALSFX_RELAY_TABLE(OALSFX_RX)
+	OALSFX_RELAY_MULTI_TABLE(OALSFX_RX)
 #undef OALSFX_RX
 #define OALSFX_SX(sid, CT) if (id == sid) return #sid;
 	OALSFX_SPAN_TABLE(OALSFX_SX)

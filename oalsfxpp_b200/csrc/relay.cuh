@@ -226,7 +226,7 @@ __device__ __forceinline__ void dispatch(const MixArgs& a, Shared<CT>& sh, float
 }
 
 template <int CT, bool HEAVY>
-__global__ void __launch_bounds__(kThreads, HEAVY ? 2 : 4) relay_kernel(const __grid_constant__ MixArgs a)
+__device__ __forceinline__ void relay_body(const MixArgs& a)
 {
 	extern __shared__ __align__(16) float dyn[];
 	__shared__ __align__(16) Shared<CT> sh;
@@ -243,6 +243,40 @@ __global__ void __launch_bounds__(kThreads, HEAVY ? 2 : 4) relay_kernel(const __
 	case 2: dispatch<CT, HEAVY, 2>(a, sh, dyn, tile, lane); break;
 	default: dispatch<CT, HEAVY, 3>(a, sh, dyn, tile, lane); break;
 	}
+}
+
+template <int CT, bool HEAVY>
+__global__ void __launch_bounds__(kThreads, HEAVY ? 2 : 4) relay_kernel(const __grid_constant__ MixArgs a)
+{
+	relay_body<CT, HEAVY>(a);
+}
+
+// One parameter class PER TILE (as duo_multi_kernel, duo.cuh): the tile's coefficient blocks and pending bits come
+// from the class table in HBM, assembled with the launch-wide arguments in shared memory.
+template <int CT, bool HEAVY>
+__global__ void __launch_bounds__(kThreads, HEAVY ? 2 : 4) relay_multi_kernel(const __grid_constant__ MixArgs a)
+{
+	__shared__ __align__(16) MixArgs sa;
+	const int tile = a.tiles ? static_cast<int>(a.tiles[blockIdx.x].tile) : a.tile_first + static_cast<int>(blockIdx.x);
+	const MixClassEntry* entry = a.class_table + a.tile_class[tile];
+	const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
+	uint32_t* ps = reinterpret_cast<uint32_t*>(&sa);
+	constexpr int kWords = static_cast<int>(sizeof(MixArgs) / 4), kCoef0 = static_cast<int>(kMixCoefOffset / 4),
+		kCoefWords = static_cast<int>(kMixCoefBytes / 4);
+	for (int i = threadIdx.x; i < kWords; i += kThreads) {
+		if (i < kCoef0 || i >= kCoef0 + kCoefWords) {
+			ps[i] = pa[i];
+		}
+	}
+	for (int i = threadIdx.x; i < kCoefWords; i += kThreads) {
+		ps[kCoef0 + i] = entry->coefs[i];
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		sa.update_mask = a.update_mask & entry->pending;
+	}
+	__syncthreads();
+	relay_body<CT, HEAVY>(sa);
 }
 
 } // namespace relay

@@ -541,6 +541,59 @@ def test_class_per_tile_launch_many_presets(checker):
         _assert_match(expect, y[s], True, f"class-per-tile stream {s}")
 
 
+@pytest.mark.parametrize("fmt", [F.mono, F.stereo])
+def test_class_per_tile_launch_on_a_relay_signature(checker, fmt):
+    """Class per tile for a signature without a fused kernel (echo, null, reverb, flanger): relay_multi_kernel, one
+    launch per block, slot positions compacted (pending bits follow), 12 classes, ragged last tile."""
+    lib = _lib()
+    names = ox.reverb_preset_names(lib=lib)
+    tiles = 12
+    S = tiles * 32 - 9
+    C = ox.channel_count(fmt)
+    blocks = [1024, 333, 1024, 640]
+    total = sum(blocks)
+    x = np.stack([H.noise(5000 + s, C, total) for s in range(S)])
+    y = np.empty_like(x)
+
+    def config(t, phase):
+        g, n = names[(5 * t + 1 + 17 * phase) % len(names)]
+        return [(T.echo, ox.default_props(T.echo, lib=lib, delay_=0.02 + 0.004 * t, feedback_=0.3 + 0.02 * t)), (T.null, None),
+                (T.eax_reverb, ox.reverb_preset(g, n, lib=lib)),
+                (T.flanger, ox.default_props(T.flanger, lib=lib, rate_=0.2 + 0.05 * t, feedback_=-0.5 + 0.05 * t + 0.1 * phase))]
+
+    with ox.Engine(S, fmt, 48000, 4, lib=lib) as eng:
+        for t in range(tiles):
+            n = min(32, S - 32 * t)
+            for slot, (et, p) in enumerate(config(t, 0)):
+                eng.set_effect(slot, et, p, first_stream=32 * t, n_streams=n)
+        at = 0
+        for b, n in enumerate(blocks):
+            if b == 2:
+                for t in range(0, tiles, 2):
+                    m = min(32, S - 32 * t)
+                    for slot, (et, p) in enumerate(config(t, 1)):
+                        if et in (T.eax_reverb, T.flanger):
+                            eng.set_effect(slot, et, p, first_stream=32 * t, n_streams=m)
+            y[:, at:at + n] = eng.mix(np.ascontiguousarray(x[:, at:at + n]))
+            at += n
+        assert eng.launch_count == len(blocks), eng.launch_count
+    for s in (0, 31, 32, 64, 100, 200, S - 1):
+        t = s // 32
+        script = []
+        for slot, (et, p) in enumerate(config(t, 0)):
+            script += [("type", slot, et)] + ([("props", slot, p)] if p is not None else [])
+        script += [("apply",)]
+        for b, n in enumerate(blocks):
+            if b == 2 and t % 2 == 0:
+                for slot, (et, p) in enumerate(config(t, 1)):
+                    if et in (T.eax_reverb, T.flanger):
+                        script += [("props", slot, p)]
+                script += [("apply",)]
+            script += [("mix", n)]
+        expect = H.run_script_orc(checker, fmt, 48000, 4, script, x[s])
+        _assert_match(expect, y[s], True, f"relay class-per-tile stream {s}")
+
+
 def test_stream_major_bus_reduce_is_exact_enough_and_deterministic():
     """The coalesced two-pass reduction (row groups of 128 streams, then the groups): equals the float64 sum
     of the per-stream outputs within 1e-5 * sqrt(S) and is bit-identical from call to call."""
