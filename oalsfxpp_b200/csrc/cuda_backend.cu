@@ -364,14 +364,14 @@ public:
 			duo::duo_multi_kernel<CT, F0, F1, F2, F3><<<static_cast<unsigned>(args.tile_count), 64, tune_dyn_smem_, st>>>(args); break;
 			OALSFX_MULTI_TABLE(OALSFX_MX)
 #undef OALSFX_MX
-#define OALSFX_SX(id, CT) \
+#define OALSFX_SX(id, CT, SL) \
 		case id: \
 			if (!carveout_done_[id]) { \
-				cudaFuncSetAttribute(span::span_reverb_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, span::shared_floats(CT) * static_cast<int>(sizeof(float))); \
+				cudaFuncSetAttribute(span::span_reverb_kernel<CT, SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, span::shared_floats(CT, SL) * static_cast<int>(sizeof(float))); \
 				carveout_done_[id] = true; \
 			} \
-			span::span_reverb_kernel<CT><<<static_cast<unsigned>(args.tile_count), span::kThreads, \
-				static_cast<size_t>(span::shared_floats(CT)) * sizeof(float), st>>>(args); break;
+			span::span_reverb_kernel<CT, SL><<<static_cast<unsigned>(args.tile_count) * (kLanes / SL), span::kThreads, \
+				static_cast<size_t>(span::shared_floats(CT, SL)) * sizeof(float), st>>>(args); break;
 			OALSFX_SPAN_TABLE(OALSFX_SX)
 #undef OALSFX_SX
 		default:

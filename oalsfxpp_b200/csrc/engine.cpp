@@ -848,7 +848,10 @@ struct oalsfx_engine {
 				const int t = span::span_frames_for(a.slot[0].u.reverb);
 				if (t > 0) {
 					a.span_frames = t;
-					return be->launch_mix(ki.id == kReverbMono ? kSpanReverbMono : kSpanReverbStereo, a, stream);
+					// few tiles: share each of them among 2 or 4 CTAs (16 / 8 streams each) while that still fits one wave
+					// of the 148 SMs (a CTA fills an SM's register file)
+					const int share = a.tile_count * 4 <= 148 ? 2 : a.tile_count * 2 <= 148 ? 1 : 0;
+					return be->launch_mix((ki.id == kReverbMono ? kSpanReverbMono : kSpanReverbStereo) + share, a, stream);
 				}
 			}
 			// Few tiles cannot fill the GPU with two warps each: below ~one tile per SM the four-stage pipeline

@@ -88,9 +88,14 @@
 	RX(kRelayMultiStereoHeavy, 2, true)
 
 // Span kernels (span.cuh): the single-reverb-slot signature block-parallel in time.  SX(id, CT).
+// SX(id, CT, SL): SL = streams of a tile per CTA (a tile is shared by 32 / SL CTAs); ids of one CT are consecutive.
 #define OALSFX_SPAN_TABLE(SX) \
-	SX(kSpanReverbMono, 1) \
-	SX(kSpanReverbStereo, 2)
+	SX(kSpanReverbMono, 1, 32) \
+	SX(kSpanReverbMono16, 1, 16) \
+	SX(kSpanReverbMono8, 1, 8) \
+	SX(kSpanReverbStereo, 2, 32) \
+	SX(kSpanReverbStereo16, 2, 16) \
+	SX(kSpanReverbStereo8, 2, 8)
 
 namespace oalsfx {
 
@@ -116,7 +121,7 @@ enum KernelId : int {
 	OALSFX_RELAY_TABLE(OALSFX_RX)
 	OALSFX_RELAY_MULTI_TABLE(OALSFX_RX)
 #undef OALSFX_RX
-#define OALSFX_SX(id, CT) id,
+#define OALSFX_SX(id, CT, SL) id,
 	OALSFX_SPAN_TABLE(OALSFX_SX)
 #undef OALSFX_SX
 #define OALSFX_MX(id, CT, F0, F1, F2, F3, duo) id,
@@ -241,7 +246,7 @@ inline const char* kernel_name(int id)
 	OALSFX_RELAY_TABLE(OALSFX_RX)
 	OALSFX_RELAY_MULTI_TABLE(OALSFX_RX)
 #undef OALSFX_RX
-#define OALSFX_SX(sid, CT) if (id == sid) return #sid;
+#define OALSFX_SX(sid, CT, SL) if (id == sid) return #sid;
 	OALSFX_SPAN_TABLE(OALSFX_SX)
 #undef OALSFX_SX
 #define OALSFX_MX(mid, CT, F0, F1, F2, F3, duo) if (id == mid) return #mid;

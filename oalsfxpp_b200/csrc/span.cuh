@@ -38,7 +38,7 @@ namespace span {
 constexpr int kWarps = 16;
 constexpr int kMaxFrames = 64;            // frames per span (shared memory is sized for this)
 constexpr int kThreads = kWarps * kLanes;
-constexpr int shared_floats(int channels) { return kMaxFrames * (12 + channels) * kLanes; }
+constexpr int shared_floats(int channels, int stream_lanes) { return kMaxFrames * (12 + channels) * stream_lanes; }
 
 // Largest span length (a multiple of 16, <= kMaxFrames) that is legal for this coefficient block, or 0.
 inline int span_frames_for(const ReverbCoef& c)
@@ -88,18 +88,27 @@ struct FxWetProbe {
 	}
 };
 
-template <int CT>
+// SL: streams of the tile one CTA handles (32, 16 or 8).  With SL < 32 a tile is shared by 32 / SL CTAs -- on as many
+// SMs -- and a warp covers FR = 32 / SL consecutive frames of those streams: lane = frame * SL + stream.  Few tiles
+// are instruction-bound on the one SM each of them gets (profiles/r01_ncu_span_top_stalls.txt); streams are
+// independent, so the split needs no communication.
+template <int CT, int SL>
 __global__ void __launch_bounds__(kThreads, 1) span_reverb_kernel(const __grid_constant__ MixArgs a)
 {
 	using R = FxReverbTail;
-	extern __shared__ __align__(16) float dyn[];  // kSharedFloats<CT> floats
-	float (*sA)[4][kLanes] = reinterpret_cast<float (*)[4][kLanes]>(dyn);                               // A-format lines before the shelves (A -> B)
-	float (*sL)[4][kLanes] = reinterpret_cast<float (*)[4][kLanes]>(dyn + kMaxFrames * 4 * kLanes);     // late lines before / after the T60 filters (A -> B -> C)
-	float (*sE)[4][kLanes] = reinterpret_cast<float (*)[4][kLanes]>(dyn + 2 * kMaxFrames * 4 * kLanes); // early line outputs (A -> C)
-	float (*sO)[CT][kLanes] = reinterpret_cast<float (*)[CT][kLanes]>(dyn + 3 * kMaxFrames * 4 * kLanes); // bus after the dry mix (A -> C)
+	constexpr int FR = kLanes / SL, SPLIT = kLanes / SL;
+	extern __shared__ __align__(16) float dyn[];  // shared_floats(CT, SL) floats, each array [line][frame][stream]
+	float* const sA = dyn;                          // A-format lines before the shelves (A -> B)
+	float* const sL = dyn + 4 * kMaxFrames * SL;    // late lines before / after the T60 filters (A -> B -> C)
+	float* const sE = dyn + 8 * kMaxFrames * SL;    // early line outputs (A -> C)
+	float* const sO = dyn + 12 * kMaxFrames * SL;   // bus after the dry mix (A -> C)
+#define OALSFX_SPAN_AT(base, line, t) base[((line) * kMaxFrames + (t)) * SL + sl]
 
-	const int tile = a.tiles ? static_cast<int>(a.tiles[blockIdx.x].tile) : a.tile_first + static_cast<int>(blockIdx.x);
-	const int lane = threadIdx.x % kLanes;
+	const int tile_slot = static_cast<int>(blockIdx.x) / SPLIT;
+	const int tile = a.tiles ? static_cast<int>(a.tiles[tile_slot].tile) : a.tile_first + tile_slot;
+	const int sl = static_cast<int>(threadIdx.x % kLanes) % SL;          // stream within this CTA's share
+	const int f = static_cast<int>(threadIdx.x % kLanes) / SL;           // frame within the warp's FR frames
+	const int lane = (static_cast<int>(blockIdx.x) % SPLIT) * SL + sl;   // stream within the tile
 	const int w = threadIdx.x / kLanes;
 	const bool io_ok = tile * kLanes + lane < a.num_streams;
 	const ReverbCoef& c = a.slot[0].u.reverb;
@@ -140,7 +149,7 @@ __global__ void __launch_bounds__(kThreads, 1) span_reverb_kernel(const __grid_c
 		}
 	}
 	if (!__syncthreads_and(ok || !io_ok)) {
-		if (w == 0 && io_ok) {
+		if (w == 0 && f == 0 && io_ok) {
 			mix_stream<CT, false, FxReverb, FxNull, FxNull, FxNull>(a, tile, lane, nullptr);
 		}
 		return;
@@ -218,7 +227,7 @@ __global__ void __launch_bounds__(kThreads, 1) span_reverb_kernel(const __grid_c
 		const float* wet = probe.fx.wet;
 #pragma unroll
 		for (int ch = 0; ch < CT; ++ch) {
-			sO[t][ch][lane] = acc[ch];
+			OALSFX_SPAN_AT(sO, ch, t) = acc[ch];
 		}
 		{
 			// B-format -> A-format, as reverb_input_stage (fx_reverb.cuh)
@@ -229,10 +238,10 @@ __global__ void __launch_bounds__(kThreads, 1) span_reverb_kernel(const __grid_c
 			const F2 p2 = f2_bcast(wet[2]) * f2(q, -q);
 			const F2 a01 = (((zero + p0) + p1) + p2) + p3;
 			const F2 a23 = (((zero + p0) + p1) - p2) - p3;
-			sA[t][0][lane] = f2_lo(a01);
-			sA[t][1][lane] = f2_hi(a01);
-			sA[t][2][lane] = f2_lo(a23);
-			sA[t][3][lane] = f2_hi(a23);
+			OALSFX_SPAN_AT(sA, 0, t) = f2_lo(a01);
+			OALSFX_SPAN_AT(sA, 1, t) = f2_hi(a01);
+			OALSFX_SPAN_AT(sA, 2, t) = f2_lo(a23);
+			OALSFX_SPAN_AT(sA, 3, t) = f2_hi(a23);
 		}
 		// early reflections (the EARLY half of FxReverbT::body)
 		F2 fa = f2(k.early[0], k.early[1]) * f2(c.early_tap_coeff[0], c.early_tap_coeff[1]);
@@ -244,10 +253,10 @@ __global__ void __launch_bounds__(kThreads, 1) span_reverb_kernel(const __grid_c
 		ring.st(eline0 + 3 * eline_len + (pos & eline_mask), f2_lo(fa));
 		fa = fa + (f2(k.eline[0], k.eline[1]) * f2(c.early_coeff[0], c.early_coeff[1]));
 		fb = fb + (f2(k.eline[2], k.eline[3]) * f2(c.early_coeff[2], c.early_coeff[3]));
-		sE[t][0][lane] = f2_lo(fa);
-		sE[t][1][lane] = f2_hi(fa);
-		sE[t][2][lane] = f2_lo(fb);
-		sE[t][3][lane] = f2_hi(fb);
+		OALSFX_SPAN_AT(sE, 0, t) = f2_lo(fa);
+		OALSFX_SPAN_AT(sE, 1, t) = f2_hi(fa);
+		OALSFX_SPAN_AT(sE, 2, t) = f2_lo(fb);
+		OALSFX_SPAN_AT(sE, 3, t) = f2_hi(fb);
 		{
 			F2 ra = fa, rb = fb;
 			R::scatter2_reversed(ra, rb, c.mix_x, c.mix_y);
@@ -262,17 +271,17 @@ __global__ void __launch_bounds__(kThreads, 1) span_reverb_kernel(const __grid_c
 		fb = f2(k.late[2], k.late[3]) * c.density_gain;
 		fa = fa + f2(k.lline[0], k.lline[1]);
 		fb = fb + f2(k.lline[2], k.lline[3]);
-		sL[t][0][lane] = f2_lo(fa);
-		sL[t][1][lane] = f2_hi(fa);
-		sL[t][2][lane] = f2_lo(fb);
-		sL[t][3][lane] = f2_hi(fb);
+		OALSFX_SPAN_AT(sL, 0, t) = f2_lo(fa);
+		OALSFX_SPAN_AT(sL, 1, t) = f2_hi(fa);
+		OALSFX_SPAN_AT(sL, 2, t) = f2_lo(fb);
+		OALSFX_SPAN_AT(sL, 3, t) = f2_hi(fb);
 	};
 	// Next span's ring rows and input rows -> L2, requested by the warps that idle during phase B.
 	auto prefetch_span = [&](int first_next) {
 		const int count = min(T, a.frames - first_next);
 		const int lap_len = c.mask[3] + 1, lap0 = c.ring_base[3], lap_mask = c.mask[3];
 		const int eap_len = c.mask[1] + 1, eap0 = c.ring_base[1], eap_mask = c.mask[1];
-		for (int t = w - 4; t < count; t += kWarps - 4) {
+		for (int t = (w - 4) * FR + f; t < count; t += (kWarps - 4) * FR) {
 			const int pos = offset0 + first_next + t;
 #pragma unroll
 			for (int l = 0; l < 4; ++l) {
@@ -292,8 +301,8 @@ __global__ void __launch_bounds__(kThreads, 1) span_reverb_kernel(const __grid_c
 	for (int first = 0; first < a.frames; first += T) {
 		const int count = min(T, a.frames - first);
 		// ---- A: everything that only reads data older than the span (two frames per iteration) ----
-		for (int t = w; t < count; t += 2 * kWarps) {
-			const int t2 = t + kWarps;
+		for (int t = w * FR + f; t < count; t += 2 * kWarps * FR) {
+			const int t2 = t + kWarps * FR;
 			const bool two = t2 < count;
 			const int pos = offset0 + first + t;
 			float x0[CT], x1[CT];
@@ -305,19 +314,19 @@ __global__ void __launch_bounds__(kThreads, 1) span_reverb_kernel(const __grid_c
 			}
 			load_taps(pos, k0);
 			if (two) {
-				load_taps(pos + kWarps, k1);
+				load_taps(pos + kWarps * FR, k1);
 			}
 			phase_a(t, pos, x0, k0);
 			if (two) {
-				phase_a(t2, pos + kWarps, x1, k1);
+				phase_a(t2, pos + kWarps * FR, x1, k1);
 			}
 		}
 		__syncthreads();
 		// ---- B: the recurrences, one warp per line pair; the other warps pull the next span into L2 ----
-		if (w < 2) {
+		if (w < 2 && f == 0) {
 			for (int t = 0; t < count; ++t) {
 				const int pos = offset0 + first + t;
-				F2 v = f2(sA[t][2 * w][lane], sA[t][2 * w + 1][lane]);
+				F2 v = f2(OALSFX_SPAN_AT(sA, 2 * w, t), OALSFX_SPAN_AT(sA, 2 * w + 1, t));
 				v = biquad_step2(c.lp, lp[0], lp[1], v);
 				if (c.is_eax) {
 					v = biquad_step2(c.hp, hp[0], hp[1], v);
@@ -325,11 +334,11 @@ __global__ void __launch_bounds__(kThreads, 1) span_reverb_kernel(const __grid_c
 				ring.st(main0 + (2 * w) * main_len + (pos & main_mask), f2_lo(v));
 				ring.st(main0 + (2 * w + 1) * main_len + (pos & main_mask), f2_hi(v));
 			}
-		} else if (w < 4) {
+		} else if (w < 4 && f == 0) {
 			const int j = 2 * (w - 2);
 			for (int t = 0; t < count; ++t) {
 				// late_t60_filter (oalsfxpp.cpp:7691-7719), as in FxReverbT::body
-				const F2 in = f2(sL[t][j][lane], sL[t][j + 1][lane]);
+				const F2 in = f2(OALSFX_SPAN_AT(sL, j, t), OALSFX_SPAN_AT(sL, j + 1, t));
 				const F2 o1 = (f2(c.t60_lf[j][0], c.t60_lf[j + 1][0]) * in) + (f2(c.t60_lf[j][1], c.t60_lf[j + 1][1]) * t60p[0][0]) +
 					(f2(c.t60_lf[j][2], c.t60_lf[j + 1][2]) * t60p[0][1]);
 				t60p[0][0] = in;
@@ -339,37 +348,37 @@ __global__ void __launch_bounds__(kThreads, 1) span_reverb_kernel(const __grid_c
 				t60p[1][0] = o1;
 				t60p[1][1] = o2;
 				const F2 out = f2(c.t60_mid[j], c.t60_mid[j + 1]) * o2;
-				sL[t][j][lane] = f2_lo(out);
-				sL[t][j + 1][lane] = f2_hi(out);
+				OALSFX_SPAN_AT(sL, j, t) = f2_lo(out);
+				OALSFX_SPAN_AT(sL, j + 1, t) = f2_hi(out);
 			}
-		} else if (first + T < a.frames) {
+		} else if (w >= 4 && first + T < a.frames) {
 			prefetch_span(first + T);
 		}
 		__syncthreads();
 		// ---- C: the rest of the late reverb, pan, output (two frames per iteration) ----
-		for (int t = w; t < count; t += 2 * kWarps) {
+		for (int t = w * FR + f; t < count; t += 2 * kWarps * FR) {
 			const int lap_len = c.mask[3] + 1, lap0 = c.ring_base[3], lap_mask = c.mask[3];
 			float tp[2][4];
 #pragma unroll
 			for (int u = 0; u < 2; ++u) {
 #pragma unroll
 				for (int l = 0; l < 4; ++l) {
-					const int pos = offset0 + first + t + u * kWarps;
-					tp[u][l] = (u == 0 || t + kWarps < count) ? ring.ld(lap0 + l * lap_len + ((pos - c.late_ap_off[l]) & lap_mask)) : 0.0F;
+					const int pos = offset0 + first + t + u * kWarps * FR;
+					tp[u][l] = (u == 0 || t + kWarps * FR < count) ? ring.ld(lap0 + l * lap_len + ((pos - c.late_ap_off[l]) & lap_mask)) : 0.0F;
 				}
 			}
 #pragma unroll
 			for (int u = 0; u < 2; ++u) {
-				const int tt = t + u * kWarps;
+				const int tt = t + u * kWarps * FR;
 				if (tt < count) {
 					const int n = first + tt;
 					const int pos = offset0 + n;
-					F2 fa = f2(sL[tt][0][lane], sL[tt][1][lane]), fb = f2(sL[tt][2][lane], sL[tt][3][lane]);
+					F2 fa = f2(OALSFX_SPAN_AT(sL, 0, tt), OALSFX_SPAN_AT(sL, 1, tt)), fb = f2(OALSFX_SPAN_AT(sL, 2, tt), OALSFX_SPAN_AT(sL, 3, tt));
 					allpass(fa, fb, tp[u], 3, pos);
 					float out8[8];
 #pragma unroll
 					for (int l = 0; l < 4; ++l) {
-						out8[l] = sE[tt][l][lane];
+						out8[l] = OALSFX_SPAN_AT(sE, l, tt);
 					}
 					out8[4] = f2_lo(fa);
 					out8[5] = f2_hi(fa);
@@ -387,7 +396,7 @@ __global__ void __launch_bounds__(kThreads, 1) span_reverb_kernel(const __grid_c
 					float acc[CT];
 #pragma unroll
 					for (int ch = 0; ch < CT; ++ch) {
-						acc[ch] = sO[tt][ch][lane];
+						acc[ch] = OALSFX_SPAN_AT(sO, ch, tt);
 					}
 #pragma unroll
 					for (int l = 0; l < 8; ++l) {
@@ -411,6 +420,9 @@ __global__ void __launch_bounds__(kThreads, 1) span_reverb_kernel(const __grid_c
 	}
 
 	// ---- state ----
+	if (f != 0) {
+		return;
+	}
 	if (w < 2) {
 #pragma unroll
 		for (int i = 0; i < 2; ++i) {
@@ -435,6 +447,8 @@ __global__ void __launch_bounds__(kThreads, 1) span_reverb_kernel(const __grid_c
 		duo::store_passthrough_history<CT>(ss, 1 + a.aux_index[0], src, a, io_ok);
 	}
 }
+
+#undef OALSFX_SPAN_AT
 
 #endif // __CUDACC__
 
