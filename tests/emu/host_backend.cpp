@@ -47,8 +47,74 @@ public:
 		}
 		return true;
 	}
-	bool launch_mix(int kernel_id, const MixArgs& a, void*) override
+	// The device-only kernel families are emulated with the thread-per-stream bodies, so that the engine's selection
+	// logic, argument assembly and class tables are exercised on the CPU as well:
+	//   span   -> the plain single-reverb kernel (same values by construction, only the schedule differs on the GPU)
+	//   relay  -> one exact single-effect pass per stage, in stage order, the running bus parked in dst
+	//             (the same additions in the same order; sanitized zero gains are simply skipped)
+	//   *multi -> tile by tile, the tile's class copied into the arguments as the kernels do in shared memory
+	bool has_relay() const override { return true; }
+	bool launch_mix(int kernel_id, const MixArgs& a, void* stream) override
 	{
+		int multi_base = -1;
+		if (kernel_id == kMultiChainStereo) {
+			multi_base = kChainStereo;
+		}
+#define OALSFX_RX(id, CT, HEAVY) if (kernel_id == id) { multi_base = (CT == 1 ? (HEAVY ? kRelayMonoHeavy : kRelayMono) : (HEAVY ? kRelayStereoHeavy : kRelayStereo)); }
+		OALSFX_RELAY_MULTI_TABLE(OALSFX_RX)
+#undef OALSFX_RX
+		if (multi_base >= 0) {
+			for (int w = 0; w < a.tile_count; ++w) {
+				const int tile = a.tiles ? static_cast<int>(a.tiles[w].tile) : a.tile_first + w;
+				const MixClassEntry& entry = a.class_table[a.tile_class[tile]];
+				MixArgs t = a;
+				std::memcpy(reinterpret_cast<char*>(&t) + kMixCoefOffset, entry.coefs, kMixCoefBytes);
+				t.update_mask = a.update_mask & entry.pending;
+				t.tiles = nullptr;
+				t.tile_first = tile;
+				t.tile_count = 1;
+				t.class_table = nullptr;
+				t.tile_class = nullptr;
+				if (!launch_mix(multi_base, t, stream)) {
+					return false;
+				}
+			}
+			return true;
+		}
+		bool is_relay = false;
+#define OALSFX_RX(id, CT, HEAVY) is_relay = is_relay || kernel_id == id;
+		OALSFX_RELAY_TABLE(OALSFX_RX)
+#undef OALSFX_RX
+		if (is_relay) {
+			static const int gen_for_kind[] = {kGenDry, kGenModDelay, kGenCompressor, kGenDedicated, kGenDistortion,
+				kGenEcho, kGenEqualizer, kGenRingMod, kGenReverb};
+			for (int p = 0; p < a.relay_count; ++p) {
+				MixArgs t = a;
+				for (int q = 0; q < kMaxSlots; ++q) {
+					t.ring[q] = nullptr;
+					t.slot_state[q] = nullptr;
+					std::memset(&t.slot[q], 0, sizeof(t.slot[q]));
+					std::memset(&t.aux[q], 0, sizeof(t.aux[q]));
+				}
+				t.with_dry = p == 0 ? 1 : 0;
+				t.accumulate = p == 0 ? 0 : 1;
+				t.update_mask = (a.update_mask >> p) & 1U;
+				t.aux_index[0] = a.aux_index[p];
+				t.ring[0] = a.ring[p];
+				t.ring_tile_stride[0] = a.ring_tile_stride[p];
+				t.slot_state[0] = a.slot_state[p];
+				t.slot[0] = a.slot[p];
+				t.aux[0] = a.aux[p];
+				t.relay_count = 0;
+				if (!launch_mix(gen_for_kind[a.relay_kind[p]], t, stream)) {
+					return false;
+				}
+			}
+			return true;
+		}
+#define OALSFX_SX(id, CT, SL) if (kernel_id == id) { kernel_id = (CT == 1 ? kReverbMono : kReverbStereo); }
+		OALSFX_SPAN_TABLE(OALSFX_SX)
+#undef OALSFX_SX
 		if (kernel_id >= kKernelCount && kernel_id < kTabDry) { // a quad / duo / quartet kernel: the CPU build runs its thread-per-stream twin
 			kernel_id = twin_of_quad(kernel_id);
 		}

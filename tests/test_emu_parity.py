@@ -163,3 +163,29 @@ def test_many_parameter_sets_table_mode(checker):
     launches, nblocks = H.many_parameter_sets(H.emu_lib(), checker, 70, 1500, 512, range(70), exact_all=True)
     # two kind signatures -> two groups of (dry+slot, 3 accumulate passes): not one launch per parameter set
     assert launches <= nblocks * 2 * 4
+
+
+# ---- the device-only kernel families, emulated by the CPU backend (tests/emu/host_backend.cpp): what is checked here
+# is the engine's host logic around them -- selection, slot compaction, legality checks, class tables, fallbacks ----
+def _gpu_scenarios(monkeypatch):
+    import test_gpu_parity as G
+    monkeypatch.setattr(G, "_lib", H.emu_lib)
+    return G
+
+
+@pytest.mark.parametrize("sig", [0, 1, 2, 6])
+def test_relay_selection_and_slot_compaction(checker, sig, monkeypatch):
+    _gpu_scenarios(monkeypatch).test_relay_pipeline_runs_any_signature_in_one_launch(checker, sig)
+
+
+@pytest.mark.parametrize("case", ["eax-mono", "short-first-blocks", "dense"])
+def test_span_selection_and_legality(checker, case, monkeypatch):
+    _gpu_scenarios(monkeypatch).test_span_kernel_on_steady_state_blocks(checker, case)
+
+
+def test_class_per_tile_tables_chain(checker, monkeypatch):
+    _gpu_scenarios(monkeypatch).test_class_per_tile_launch_many_presets(checker)
+
+
+def test_class_per_tile_tables_relay(checker, monkeypatch):
+    _gpu_scenarios(monkeypatch).test_class_per_tile_launch_on_a_relay_signature(checker, F.mono)
