@@ -324,6 +324,7 @@ __global__ void __launch_bounds__(kThreads, 1) span_reverb_kernel(const __grid_c
 		__syncthreads();
 		// ---- B: the recurrences, one warp per line pair; the other warps pull the next span into L2 ----
 		if (w < 2 && f == 0) {
+#pragma unroll 4
 			for (int t = 0; t < count; ++t) {
 				const int pos = offset0 + first + t;
 				F2 v = f2(OALSFX_SPAN_AT(sA, 2 * w, t), OALSFX_SPAN_AT(sA, 2 * w + 1, t));
@@ -336,6 +337,7 @@ __global__ void __launch_bounds__(kThreads, 1) span_reverb_kernel(const __grid_c
 			}
 		} else if (w < 4 && f == 0) {
 			const int j = 2 * (w - 2);
+#pragma unroll 4
 			for (int t = 0; t < count; ++t) {
 				// late_t60_filter (oalsfxpp.cpp:7691-7719), as in FxReverbT::body
 				const F2 in = f2(OALSFX_SPAN_AT(sL, j, t), OALSFX_SPAN_AT(sL, j + 1, t));
