@@ -398,23 +398,17 @@ struct oalsfx_engine {
 			}
 		}
 		const size_t padded = static_cast<size_t>(tiles) * kLanes;
-		size_t lane_cap = lane_send_dev ? padded : 0;
 		if (!grow(slot_table_dev, slot_table_cap, coefs.size()) || !grow(send_table_dev, send_table_cap, sends.size())) {
 			return false;
 		}
-		if (!lane_send_dev) {
-			lane_send_dev = static_cast<int32_t*>(dev_alloc(padded * sizeof(int32_t)));
-			for (int s = 0; s < kMaxSlots; ++s) {
-				lane_class_dev[s] = static_cast<int32_t*>(dev_alloc(padded * sizeof(int32_t)));
-				if (!lane_class_dev[s]) {
-					return false;
-				}
-			}
-			if (!lane_send_dev) {
+		if (!lane_send_dev && !(lane_send_dev = static_cast<int32_t*>(dev_alloc(padded * sizeof(int32_t))))) {
+			return false;
+		}
+		for (int s = 0; s < kMaxSlots; ++s) {
+			if (!lane_class_dev[s] && !(lane_class_dev[s] = static_cast<int32_t*>(dev_alloc(padded * sizeof(int32_t))))) {
 				return false;
 			}
 		}
-		(void)lane_cap;
 		bool ok = be->upload(slot_table_dev, coefs.data(), coefs.size() * sizeof(SlotCoef), nullptr) &&
 			be->upload(send_table_dev, sends.data(), sends.size() * sizeof(SendCoef), nullptr);
 		std::vector<int32_t> idx(padded, 0);
