@@ -143,6 +143,7 @@ struct FxReverbT {
 	bool primed, can_pf;
 	int32_t pf_row4;   // window row of the first position of the batch holding the current position
 	bool pan_static;   // this sub-chunk: no gain ramps and every one of the 8 x C pan gains is audible
+	bool pan_ramp_all; // this sub-chunk: every one of this instance's pan gains ramps (a gain change: all of them scale)
 	uint32_t direct_groups; // this sub-chunk: tap groups (bit = OLD-tap group id) the window cannot serve, read in place
 
 	unsigned pf_s;     // shared-space address of the warp's window (lane offset removed), device build
@@ -272,6 +273,7 @@ struct FxReverbT {
 		can_pf = ok;
 		direct_groups = direct;
 		pan_static = true;
+		pan_ramp_all = true;
 		const int counter = block_frames - base;
 		const float delta = 1.0F / static_cast<float>(counter);
 		ramp_mask[0] = ramp_mask[1] = 0;
@@ -291,6 +293,7 @@ struct FxReverbT {
 						pan_static = false;
 					} else {
 						step_gain[l][k] = 0.0F;
+						pan_ramp_all = false;
 						if (audible(gain)) {
 							active_mask[l >> 2] |= bit;
 						} else {
@@ -660,6 +663,19 @@ struct FxReverbT {
 					if (CT || k < channels) {
 						acc[k] += d * cur_gain[l][k];
 					}
+				}
+			}
+			return;
+		}
+		if (pan_ramp_all && CT != 0) {
+			// every gain ramps (MixHelpers::mix, oalsfxpp.cpp:2769-2777): the general loop below without its tests
+			OALSFX_UNROLL
+			for (int l = kLine0; l < kLine1; ++l) {
+				const float d = (l < 4 ? early_out[l] : late_out[l - 4]);
+				OALSFX_UNROLL
+				for (int k = 0; k < CT; ++k) {
+					acc[k] += d * cur_gain[l][k];
+					cur_gain[l][k] += step_gain[l][k];
 				}
 			}
 			return;
