@@ -130,49 +130,47 @@ __device__ __forceinline__ void stage(const MixArgs& a, Shared<CT>& sh, float* d
 			quartet::wait_empty<HN>(b);
 		}
 		for (int f = 0; f < count; ++f) {
-			{
-				const int i = first + f;
-				float x[CT], acc[CT];
-				if (!kReverb) {
-					r.fx.prefetch_next(a.slot[P]);
-					issue_input(i + kFwDepth);
-					cp_async_commit_group();
-					cp_async_wait_group<kFwDepth>();
+			const int i = first + f;
+			float x[CT], acc[CT];
+			if (!kReverb) {
+				r.fx.prefetch_next(a.slot[P]);
+				issue_input(i + kFwDepth);
+				cp_async_commit_group();
+				cp_async_wait_group<kFwDepth>();
+			}
+			if (P == 0) {
+#pragma unroll
+				for (int c = 0; c < CT; ++c) {
+					x[c] = io_ok ? sh.win_in[i & (kFwSlots - 1)][c][lane] : 0.0F;
+					acc[c] = 0.0F;
 				}
-				if (P == 0) {
+				// direct send (oalsfxpp.cpp:2924-2950); gains sanitized by the host
+#pragma unroll
+				for (int c = 0; c < CT; ++c) {
+					pan_add<CT, true>(acc, CT, a.direct.gains[c], x[c]);
+				}
+			} else {
+#pragma unroll
+				for (int c = 0; c < CT; ++c) {
+					x[c] = sh.xch[HP][b][f][c][lane];
+					acc[c] = sh.xch[HP][b][f][CT + c][lane];
+				}
+			}
+			r.step(a, P, x, acc);
+			if (last && !fast_out) {
+				if (io_ok) {
 #pragma unroll
 					for (int c = 0; c < CT; ++c) {
-						x[c] = io_ok ? sh.win_in[i & (kFwSlots - 1)][c][lane] : 0.0F;
-						acc[c] = 0.0F;
-					}
-					// direct send (oalsfxpp.cpp:2924-2950); gains sanitized by the host
-#pragma unroll
-					for (int c = 0; c < CT; ++c) {
-						pan_add<CT, true>(acc, CT, a.direct.gains[c], x[c]);
-					}
-				} else {
-#pragma unroll
-					for (int c = 0; c < CT; ++c) {
-						x[c] = sh.xch[HP][b][f][c][lane];
-						acc[c] = sh.xch[HP][b][f][CT + c][lane];
+						dst[i * a.io_fs + c * a.io_cs] = acc[c];
 					}
 				}
-				r.step(a, P, x, acc);
-				if (last && !fast_out) {
-					if (io_ok) {
+			} else {
 #pragma unroll
-						for (int c = 0; c < CT; ++c) {
-							dst[i * a.io_fs + c * a.io_cs] = acc[c];
-						}
+				for (int c = 0; c < CT; ++c) {
+					if (!last) {
+						sh.xch[P][b][f][c][lane] = x[c];
 					}
-				} else {
-#pragma unroll
-					for (int c = 0; c < CT; ++c) {
-						if (!last) {
-							sh.xch[P][b][f][c][lane] = x[c];
-						}
-						sh.xch[P][b][f][CT + c][lane] = acc[c];
-					}
+					sh.xch[P][b][f][CT + c][lane] = acc[c];
 				}
 			}
 		}

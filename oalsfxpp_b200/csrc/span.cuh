@@ -6,7 +6,7 @@
 // sample-to-sample recurrences that do NOT are eight short IIR filters (the input shelves, oalsfxpp.cpp:
 // 7821-7832, and the late lines' T60 filters, :7691-7719).  So, in the steady state of a preset, a SPAN of
 // T consecutive frames (T <= the shortest delay) is processed in three phases by the 16 warps of a CTA,
-// lanes = the 32 streams of the tile, warps = time:
+// lanes = streams of the tile (all 32, or 16 / 8 of them when the tile is shared by 2 / 4 CTAs), warps = time:
 //
 //   A  (parallel over frames)  dry mix, wet encode, B->A conversion -> shared memory;
 //                              the whole early-reflection stage (reads only data older than the span);
