@@ -229,7 +229,7 @@ def test_pipelined_kernels_on_reverb_corner_cases(checker, family, variant, monk
         _assert_match(expect, y[s], True, f"{family} {variant} stream {s}")
 
 
-@pytest.mark.parametrize("family", ["quartet", "duo"])
+@pytest.mark.parametrize("family", ["quartet", "duo", "relay"])
 def test_pipelined_kernels_under_load_are_race_free(checker, family, monkeypatch):
     """16 384 streams (512 tiles: several waves of CTAs, every SM busy) with zero reverb delays, i.e. the
     configuration in which a stage reads, in the same frame, what the previous stage's warp has just written.
@@ -328,6 +328,39 @@ def test_span_kernel_on_steady_state_blocks(checker, case):
     for s in (0, 31, 32, 63, 64, S - 1):
         expect = H.run_script_orc(checker, fmt, rate, 1, script, x[s])
         _assert_match(expect, y[s], True, f"span {case} stream {s}")
+
+
+@pytest.mark.parametrize("tiles", [8, 50, 100])
+def test_span_kernel_every_tile_share(checker, tiles):
+    """The span kernel shares a tile among 4 / 2 / 1 CTAs depending on the tile count (8 / 16 / 32 streams per CTA):
+    8, 50 and 100 tiles pick the three variants.  Every stream is fed one of four inputs; all copies must agree bit
+    for bit and equal the checker, over steady-state blocks of odd sizes (the first block carries the update)."""
+    import torch
+    lib = _lib()
+    S = tiles * 32
+    blocks = [256, 1024, 333, 1024]
+    total = sum(blocks)
+    base = [H.noise(7000 + s, 1, total) for s in range(4)]
+    dev = torch.device("cuda:0")
+    outs = []
+    with ox.Engine(S, F.mono, 48000, 1, lib=lib) as eng:
+        eng.set_effect(0, T.eax_reverb)
+        at = 0
+        for n in blocks:
+            xb = torch.from_numpy(np.stack([v[at:at + n] for v in base])).to(dev)
+            x = xb.repeat(S // 4, 1, 1).contiguous()
+            y = torch.empty_like(x)
+            eng.mix(x, y, frames=n, stream=torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            outs.append(y)
+            at += n
+    y = torch.cat(outs, dim=1)
+    per = y.view(S // 4, 4, total, 1)
+    assert bool((per == per[0:1]).all()), "streams with identical input diverged"
+    script = [("type", 0, T.eax_reverb), ("apply",)] + [("mix", n) for n in blocks]
+    for k in range(4):
+        expect = H.run_script_orc(checker, F.mono, 48000, 1, script, base[k])
+        _assert_match(expect, per[0, k].cpu().numpy(), True, f"span share, {tiles} tiles, input {k}")
 
 
 RELAY_SIGNATURES = [
