@@ -12,11 +12,7 @@
 
 #include "backend.h"
 #include "kernel_table.h"
-#include "quad.cuh"
-#include "duo.cuh"
-#include "quartet.cuh"
-#include "relay.cuh"
-#include "span.cuh"
+#include "launch.h"
 
 namespace oalsfx {
 namespace {
@@ -316,107 +312,15 @@ public:
 			return false;
 		}
 		cudaStream_t st = static_cast<cudaStream_t>(stream);
-		constexpr int threads = 64;
-		const unsigned blocks = static_cast<unsigned>((static_cast<long long>(args.tile_count) * kLanes + threads - 1) / threads);
-		switch (kernel_id) {
-#define OALSFX_X(id, CT, SF, F0, F1, F2, F3) \
-		case id: mix_kernel<CT, SF, F0, F1, F2, F3><<<blocks, threads, 0, st>>>(args); break;
-			OALSFX_KERNEL_TABLE(OALSFX_X)
-#undef OALSFX_X
-#define OALSFX_QX(id, CT, Q0, Q1, Q2, Q3, twin) \
-		case id: quad::quad_kernel<CT, quad::Q0, quad::Q1, quad::Q2, quad::Q3> \
-			<<<static_cast<unsigned>(args.tile_count), 128, 0, st>>>(args); break;
-			OALSFX_QUAD_TABLE(OALSFX_QX)
-#undef OALSFX_QX
-#define OALSFX_DX(id, CT, F0, F1, F2, F3, twin) \
-		case id: \
-			prefer_shared(id, duo::duo_kernel<CT, F0, F1, F2, F3>, 50); \
-			duo::duo_kernel<CT, F0, F1, F2, F3><<<static_cast<unsigned>(args.tile_count), 64, tune_dyn_smem_, st>>>(args); break;
-			OALSFX_DUO_TABLE(OALSFX_DX)
-#undef OALSFX_DX
-#define OALSFX_TX(id, CT, F0, F1, F2, F3, twin) \
-		case id: \
-			prefer_shared(id, quartet::quartet_kernel<CT, F0, F1, F2, F3>, 70); \
-			quartet::quartet_kernel<CT, F0, F1, F2, F3><<<static_cast<unsigned>(args.tile_count), quartet::kThreads, tune_dyn_smem_, st>>>(args); break;
-			OALSFX_QUARTET_TABLE(OALSFX_TX)
-#undef OALSFX_TX
-#define OALSFX_TBX(id, Fx, kind) \
-		case id: mix_kernel<0, true, Fx, FxNull, FxNull, FxNull, true><<<blocks, threads, 0, st>>>(args); break;
-			OALSFX_TABMODE_TABLE(OALSFX_TBX)
-#undef OALSFX_TBX
-#define OALSFX_RX(id, CT, HEAVY) \
-		case id: \
-			relay_attributes(id, relay::relay_kernel<CT, HEAVY>); \
-			relay::relay_kernel<CT, HEAVY><<<static_cast<unsigned>(args.tile_count), relay::kThreads, \
-				static_cast<size_t>(args.relay_smem_floats) * sizeof(float), st>>>(args); break;
-			OALSFX_RELAY_TABLE(OALSFX_RX)
-#undef OALSFX_RX
-#define OALSFX_RX(id, CT, HEAVY) \
-		case id: \
-			relay_attributes(id, relay::relay_multi_kernel<CT, HEAVY>); \
-			relay::relay_multi_kernel<CT, HEAVY><<<static_cast<unsigned>(args.tile_count), relay::kThreads, \
-				static_cast<size_t>(args.relay_smem_floats) * sizeof(float), st>>>(args); break;
-			OALSFX_RELAY_MULTI_TABLE(OALSFX_RX)
-#undef OALSFX_RX
-#define OALSFX_MX(id, CT, F0, F1, F2, F3, duo_id) \
-		case id: \
-			prefer_shared(id, duo::duo_multi_kernel<CT, F0, F1, F2, F3>, 50); \
-			duo::duo_multi_kernel<CT, F0, F1, F2, F3><<<static_cast<unsigned>(args.tile_count), 64, tune_dyn_smem_, st>>>(args); break;
-			OALSFX_MULTI_TABLE(OALSFX_MX)
-#undef OALSFX_MX
-#define OALSFX_SX(id, CT, SL) \
-		case id: \
-			if (!carveout_done_[id]) { \
-				cudaFuncSetAttribute(span::span_reverb_kernel<CT, SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, span::shared_floats(CT, SL) * static_cast<int>(sizeof(float))); \
-				carveout_done_[id] = true; \
-			} \
-			span::span_reverb_kernel<CT, SL><<<static_cast<unsigned>(args.tile_count) * (kLanes / SL), span::kThreads, \
-				static_cast<size_t>(span::shared_floats(CT, SL)) * sizeof(float), st>>>(args); break;
-			OALSFX_SPAN_TABLE(OALSFX_SX)
-#undef OALSFX_SX
-		default:
+		if (!(launch_duo_family(kernel_id, args, st) || launch_span_family(kernel_id, args, st) || launch_quartet_family(kernel_id, args, st) ||
+				launch_relay_family(kernel_id, args, st) || launch_mix_family(kernel_id, args, st))) {
 			error_ = "unknown kernel id";
 			return false;
 		}
 		return check(cudaGetLastError(), kernel_name(kernel_id));
 	}
 
-	// The duo kernels stream through per-warp shared-memory windows (~25 KB per CTA) AND lean on L1:
-	// the stream-major input rows are read 4 bytes per lane per frame, so each 128-byte line serves 16
-	// consecutive frames from L1.  Measured on B200 (gpurun_out/exp13, exp21; 65 536 streams): the optimum
-	// is 4 CTAs per SM with the rest of the 228 KB as L1 (carve-out 46-54 %: 3.07 ms); 5 CTAs (62-80 %) 3.23 ms;
-	// 6 CTAs / ~28 KB of L1 (100 %) 3.8 ms; 3 CTAs 3.2 ms.
 	bool has_relay() const override { return true; }
-
-	// Relay kernels: up to four reverb windows of dynamic shared memory (96 KB), carve-out as large as needed.
-	template <class K> void relay_attributes(int id, K kernel)
-	{
-		if (!carveout_done_[id]) {
-			cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSlots * kPfWarpFloats * static_cast<int>(sizeof(float)));
-			cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-			carveout_done_[id] = true;
-		}
-	}
-
-	template <class K> void prefer_shared(int id, K kernel, int default_carveout)
-	{
-		if (!carveout_done_[id]) {
-			// tuning knobs (experiments only): OALSFX_TUNE_CARVEOUT = percent or -1 (driver default),
-			// OALSFX_TUNE_DYN_SMEM = bytes of unused dynamic shared memory per CTA (caps residency)
-			int carveout = default_carveout;
-			if (const char* e = getenv("OALSFX_TUNE_CARVEOUT")) {
-				carveout = atoi(e);
-			}
-			if (const char* e = getenv("OALSFX_TUNE_DYN_SMEM")) {
-				tune_dyn_smem_ = static_cast<size_t>(atoi(e));
-				cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tune_dyn_smem_));
-			}
-			if (carveout >= 0) {
-				cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
-			}
-			carveout_done_[id] = true;
-		}
-	}
 
 	bool reduce_bus(const float* data, long long ts, long long ls, long long fs, long long cs,
 		int num_streams, int frames, int channels, float* bus, void* stream) override
@@ -543,8 +447,6 @@ private:
 	std::string error_;
 	std::vector<cudaEvent_t> events_;
 	size_t next_event_ = 0;
-	bool carveout_done_[kKernelEnd] = {};
-	size_t tune_dyn_smem_ = 0;
 	void* bus_partial_ = nullptr;      // row-group partial sums of the bus reduction
 	size_t bus_partial_bytes_ = 0;
 };

@@ -122,8 +122,8 @@ struct oalsfx_engine {
 	// Which fused kernel family serves whole-tile groups: 2 = automatic (default): the two-stage duo kernel,
 	// or the four-stage quartet pipeline when the group has too few tiles to fill the GPU (and for
 	// signatures that only have a quartet entry); 3 = quartet wherever it exists; 4 = duo wherever it exists;
-	// 1 = quad, 0 = the plain thread-per-stream twin, 5 = the relay pipeline wherever eligible.
-	// 6 = as automatic (names the span kernel's tests).  OALSFX_KERNEL=auto|quartet|duo|quad|single|relay|span overrides
+	// 0 = the plain thread-per-stream twin, 5 = the relay pipeline wherever eligible.
+	// 6 = as automatic (names the span kernel's tests).  OALSFX_KERNEL=auto|quartet|duo|single|relay|span overrides
 	// (A/B measurements and the parity tests of every family).
 	int family = 2;
 	// Host-buffer mix: tile slice the next launches are restricted to (0 = all tiles), and the
@@ -830,7 +830,6 @@ struct oalsfx_engine {
 				}
 			}
 			++launches;
-			// All lanes of every tile take part (ragged tail apart): the 4-lanes-per-stream kernel.
 			sanitize_gains(a);
 			const bool whole_tiles = g.identity || g.full_tiles;
 			int id = ki.id;
@@ -861,10 +860,6 @@ struct oalsfx_engine {
 				id = duo_for_twin(ki.id);
 			} else if (whole_tiles && family >= 2 && quartet_for_twin(ki.id) >= 0) {
 				id = quartet_for_twin(ki.id); // no duo entry for this signature (single reverb slot)
-			} else if (whole_tiles && (family == 1 || (family >= 2 && few_tiles)) && quad_for_twin(ki.id) >= 0) {
-				// four lanes per stream: only pays when tiles are scarce (cfg3's chain, B200: 32 tiles 1.08 ms vs 1.19
-				// thread-per-stream; 512 tiles 1.46 vs 1.39; 2048 tiles 4.4 vs 1.8)
-				id = quad_for_twin(ki.id);
 			}
 			return be->launch_mix(id, a, stream);
 		}
@@ -941,7 +936,7 @@ int oalsfx_engine_create(const oalsfx_engine_desc* desc, oalsfx_engine** out)
 	e->channels = dev.channels;
 	e->slots = desc->effect_count;
 	if (const char* fam = std::getenv("OALSFX_KERNEL")) {
-		e->family = (std::strcmp(fam, "single") == 0 ? 0 : std::strcmp(fam, "quad") == 0 ? 1 : std::strcmp(fam, "quartet") == 0 ? 3 : std::strcmp(fam, "duo") == 0 ? 4 : std::strcmp(fam, "relay") == 0 ? 5 : std::strcmp(fam, "span") == 0 ? 6 : 2);
+		e->family = (std::strcmp(fam, "single") == 0 ? 0 : std::strcmp(fam, "quartet") == 0 ? 3 : std::strcmp(fam, "duo") == 0 ? 4 : std::strcmp(fam, "relay") == 0 ? 5 : std::strcmp(fam, "span") == 0 ? 6 : 2);
 	}
 	e->be = make_backend(desc->device, g_create_error);
 	if (!e->be) {

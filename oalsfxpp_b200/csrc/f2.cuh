@@ -19,7 +19,7 @@
 namespace oalsfx {
 
 #if defined(__CUDACC__)
-__constant__ unsigned long long kF2NegZero = 0x8000000080000000ULL; // (-0.0f, -0.0f)
+static __constant__ unsigned long long kF2NegZero = 0x8000000080000000ULL; // (-0.0f, -0.0f)
 #endif
 
 #if defined(__CUDA_ARCH__)

@@ -1,0 +1,43 @@
+// k_relay.cu -- the relay pipelines (relay.cuh): any slot signature, one warp per non-null slot.
+#include "launch.h"
+#include "relay.cuh"
+
+namespace oalsfx {
+
+namespace {
+// Up to four reverb windows of dynamic shared memory (96 KB), carve-out as large as needed.
+template <class K>
+void relay_attributes(bool& done, K kernel)
+{
+	if (!done) {
+		cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSlots * kPfWarpFloats * static_cast<int>(sizeof(float)));
+		cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+		done = true;
+	}
+}
+} // namespace
+
+bool launch_relay_family(int kernel_id, const MixArgs& args, cudaStream_t st)
+{
+	static bool done[kKernelEnd] = {};
+	const size_t dyn = static_cast<size_t>(args.relay_smem_floats) * sizeof(float);
+	switch (kernel_id) {
+#define OALSFX_RX(id, CT, HEAVY) \
+	case id: \
+		relay_attributes(done[id], relay::relay_kernel<CT, HEAVY>); \
+		relay::relay_kernel<CT, HEAVY><<<static_cast<unsigned>(args.tile_count), relay::kThreads, dyn, st>>>(args); \
+		return true;
+		OALSFX_RELAY_TABLE(OALSFX_RX)
+#undef OALSFX_RX
+#define OALSFX_RX(id, CT, HEAVY) \
+	case id: \
+		relay_attributes(done[id], relay::relay_multi_kernel<CT, HEAVY>); \
+		relay::relay_multi_kernel<CT, HEAVY><<<static_cast<unsigned>(args.tile_count), relay::kThreads, dyn, st>>>(args); \
+		return true;
+		OALSFX_RELAY_MULTI_TABLE(OALSFX_RX)
+#undef OALSFX_RX
+	default: return false;
+	}
+}
+
+} // namespace oalsfx

@@ -33,16 +33,6 @@
 	/* cfg0: one echo slot, stereo */ \
 	X(kEchoStereo, 2, false, FxEcho, FxNull, FxNull, FxNull)
 
-// Quad kernels (quad.cuh: four lanes per stream, next-sample prefetch) -- the throughput path.
-// QX(id, CT, Q0, Q1, Q2, Q3, twin): `twin` is the thread-per-stream entry with the same signature;
-// the engine launches the quad kernel instead of its twin whenever every tile of the group takes
-// part with all its lanes.  (The CPU test build has no quad kernels and runs the twin.)
-#define OALSFX_QUAD_TABLE(QX) \
-	QX(kQuadChainStereo, 2, QEqualizer, QModDelay, QEcho, QReverb, kChainStereo) \
-	QX(kQuadChain2Mono, 1, QModDelay, QRingMod, QDistortion, QCompressor, kChain2Mono) \
-	QX(kQuadReverbMono, 1, QReverb, QNull, QNull, QNull, kReverbMono) \
-	QX(kQuadEchoStereo, 2, QEcho, QNull, QNull, QNull, kEchoStereo)
-
 // Duo kernels (duo.cuh: thread per stream, front warp = dry + slots 0..2, back warp = slot 3 +
 // output, shared-memory hand-off).  DX(id, CT, F0, F1, F2, F3, twin), same twin rule as above.
 #define OALSFX_DUO_TABLE(DX) \
@@ -104,10 +94,7 @@ enum KernelId : int {
 	OALSFX_KERNEL_TABLE(OALSFX_X)
 #undef OALSFX_X
 	kKernelCount,
-	kQuadFirst = kKernelCount - 1,
-#define OALSFX_QX(id, CT, Q0, Q1, Q2, Q3, twin) id,
-	OALSFX_QUAD_TABLE(OALSFX_QX)
-#undef OALSFX_QX
+	kFusedFirst = kKernelCount - 1,
 #define OALSFX_DX(id, CT, F0, F1, F2, F3, twin) id,
 	OALSFX_DUO_TABLE(OALSFX_DX)
 #undef OALSFX_DX
@@ -148,24 +135,13 @@ inline int duo_for_twin(int twin_id)
 	return -1;
 }
 
-// quad kernel id for a thread-per-stream twin id, or -1
-inline int quad_for_twin(int twin_id)
+// thread-per-stream twin of a duo / quartet kernel id, or -1
+inline int twin_of_fused(int fused_id)
 {
-#define OALSFX_QX(id, CT, Q0, Q1, Q2, Q3, twin) if (twin_id == twin) return id;
-	OALSFX_QUAD_TABLE(OALSFX_QX)
-#undef OALSFX_QX
-	return -1;
-}
-
-inline int twin_of_quad(int quad_id)
-{
-#define OALSFX_QX(id, CT, Q0, Q1, Q2, Q3, twin) if (quad_id == id) return twin;
-	OALSFX_QUAD_TABLE(OALSFX_QX)
-#undef OALSFX_QX
-#define OALSFX_DX(id, CT, F0, F1, F2, F3, twin) if (quad_id == id) return twin;
+#define OALSFX_DX(id, CT, F0, F1, F2, F3, twin) if (fused_id == id) return twin;
 	OALSFX_DUO_TABLE(OALSFX_DX)
 #undef OALSFX_DX
-#define OALSFX_TX(id, CT, F0, F1, F2, F3, twin) if (quad_id == id) return twin;
+#define OALSFX_TX(id, CT, F0, F1, F2, F3, twin) if (fused_id == id) return twin;
 	OALSFX_QUARTET_TABLE(OALSFX_TX)
 #undef OALSFX_TX
 	return -1;
@@ -230,9 +206,6 @@ inline const char* kernel_name(int id)
 	if (id >= 0 && id < kKernelCount) {
 		return kernel_infos()[id].name;
 	}
-#define OALSFX_QX(qid, CT, Q0, Q1, Q2, Q3, twin) if (id == qid) return #qid;
-	OALSFX_QUAD_TABLE(OALSFX_QX)
-#undef OALSFX_QX
 #define OALSFX_DX(did, CT, F0, F1, F2, F3, twin) if (id == did) return #did;
 	OALSFX_DUO_TABLE(OALSFX_DX)
 #undef OALSFX_DX

@@ -115,8 +115,8 @@ public:
 #define OALSFX_SX(id, CT, SL) if (kernel_id == id) { kernel_id = (CT == 1 ? kReverbMono : kReverbStereo); }
 		OALSFX_SPAN_TABLE(OALSFX_SX)
 #undef OALSFX_SX
-		if (kernel_id >= kKernelCount && kernel_id < kTabDry) { // a quad / duo / quartet kernel: the CPU build runs its thread-per-stream twin
-			kernel_id = twin_of_quad(kernel_id);
+		if (kernel_id >= kKernelCount && kernel_id < kTabDry) { // a duo / quartet kernel: the CPU build runs its thread-per-stream twin
+			kernel_id = twin_of_fused(kernel_id);
 		}
 		for (int w = 0; w < a.tile_count; ++w) {
 			int tile = a.tile_first + w;

@@ -153,7 +153,7 @@ def test_cfg2_schedule_on_4096_streams(checker):
         _assert_match(expect, y[s], True, f"stream {s}")
 
 
-@pytest.mark.parametrize("family", ["quartet", "duo", "quad", "single", "relay"])
+@pytest.mark.parametrize("family", ["quartet", "duo", "single", "relay"])
 def test_every_kernel_family_on_the_chain(checker, family, monkeypatch):
     """The fused 4-slot stereo chain has four implementations (OALSFX_KERNEL, read when an engine is
     created): the two-stage duo kernel (default), the four-stage quartet pipeline, the 4-lanes-per-stream
@@ -265,7 +265,7 @@ def test_pipelined_kernels_under_load_are_race_free(checker, family, monkeypatch
 
 
 @pytest.mark.parametrize("fmt", [F.mono, F.stereo])
-@pytest.mark.parametrize("family", ["quartet", "quad", "single", "span"])
+@pytest.mark.parametrize("family", ["quartet", "single", "span"])
 def test_every_kernel_family_on_the_single_reverb_slot(checker, family, fmt, monkeypatch):
     """cfg1's signature (one reverb slot, mono): pipeline (default), quad and plain kernels, with a preset
     change mid-stream (tap cross-fade + gain ramp), a modulated preset and odd block sizes."""
