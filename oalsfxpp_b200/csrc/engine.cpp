@@ -82,6 +82,10 @@ struct oalsfx_engine {
 	std::vector<int> fx_class[kMaxSlots];
 	std::vector<int> send_class;
 	std::vector<uint8_t> pending;       // bit s: slot s has an un-consumed `update`
+	// Frames mixed since a launch last carried an update (or the engine was created / restored): a hint for the
+	// kernels that only run streams in the steady state (span.cuh) -- a reverb's tap cross-fade takes 128 frames
+	// from its update on.  The device checks the real per-stream state; this only avoids launches that would fall back.
+	long long frames_since_update = 0;
 
 	std::vector<FxClass> classes;
 	std::unordered_map<std::string, int> class_index;
@@ -833,18 +837,19 @@ struct oalsfx_engine {
 			sanitize_gains(a);
 			const bool whole_tiles = g.identity || g.full_tiles;
 			int id = ki.id;
-			// The single-reverb-slot signature with few tiles: block-parallel in time (span.cuh) whenever no update
-			// is pending and the preset's delays allow a span (the device verifies the stream state and falls back).
-			constexpr int kSpanMaxTiles = 160;
-			if ((ki.id == kReverbMono || ki.id == kReverbStereo) && whole_tiles && be->has_relay() && (family == 2 || family == 6) &&
-				a.update_mask == 0 && a.tile_count <= kSpanMaxTiles && slice_count == 0) {
-				const int t = span::span_frames_for(a.slot[0].u.reverb);
+			// Few tiles: block-parallel in time (span.cuh) for the single reverb slot and for the 4-slot chain, whenever no
+			// update is pending and the delays allow a span (the device verifies the stream state and falls back).
+			// A CTA fills an SM, so beyond one wave of the 148 SMs the kernel pays whole extra waves; few enough tiles are
+			// shared among 2 or 4 CTAs each (16 / 8 streams per CTA).
+			constexpr int kSpanMaxTiles = 296;
+			const bool span_chain = ki.id == kChainStereo;
+			if ((ki.id == kReverbMono || ki.id == kReverbStereo || span_chain) && whole_tiles && be->has_relay() && (family == 2 || family == 6) &&
+				a.update_mask == 0 && a.tile_count <= kSpanMaxTiles && slice_count == 0 && frames_since_update >= 128) {
+				const int share = a.tile_count * 4 <= 148 ? 2 : a.tile_count * 2 <= 148 ? 1 : 0;
+				const int t = span::plan_frames(a, span_chain, kLanes >> share);
 				if (t > 0) {
 					a.span_frames = t;
-					// few tiles: share each of them among 2 or 4 CTAs (16 / 8 streams each) while that still fits one wave
-					// of the 148 SMs (a CTA fills an SM's register file)
-					const int share = a.tile_count * 4 <= 148 ? 2 : a.tile_count * 2 <= 148 ? 1 : 0;
-					return be->launch_mix((ki.id == kReverbMono ? kSpanReverbMono : kSpanReverbStereo) + share, a, stream);
+					return be->launch_mix((span_chain ? kSpanChainStereo : ki.id == kReverbMono ? kSpanReverbMono : kSpanReverbStereo) + share, a, stream);
 				}
 			}
 			// Few tiles cannot fill the GPU with two warps each: below ~one tile per SM the four-stage pipeline
@@ -1144,7 +1149,9 @@ int oalsfx_engine_mix(oalsfx_engine* e, int frames, const float* src, float* dst
 				if (g.key.pending != 0) {
 					std::fill(e->pending.begin(), e->pending.end(), static_cast<uint8_t>(0));
 					e->groups_dirty = true;
+					e->frames_since_update = 0;
 				}
+				e->frames_since_update += frames;
 				return OALSFX_OK;
 			}
 		}
@@ -1173,7 +1180,9 @@ int oalsfx_engine_mix(oalsfx_engine* e, int frames, const float* src, float* dst
 		if (had_pending) {
 			std::fill(e->pending.begin(), e->pending.end(), static_cast<uint8_t>(0));
 			e->groups_dirty = true;
+			e->frames_since_update = 0;
 		}
+		e->frames_since_update += todo;
 		first_block = false;
 		done += todo;
 	}
@@ -1340,6 +1349,7 @@ int oalsfx_engine_restore(oalsfx_engine* e, const void* src, size_t bytes)
 	std::memcpy(e->pending.data(), in, static_cast<size_t>(e->streams));
 	in += e->streams;
 	e->groups_dirty = true;
+	e->frames_since_update = 128; // unknown history: let the steady-state kernels try (they check the stream state)
 	bool ok = true;
 	for (int s = 0; s < e->slots && ok; ++s) {
 		const size_t ring_bytes = static_cast<size_t>(e->tiles) * static_cast<size_t>(e->ring_cap[s]) * kLanes * sizeof(float);

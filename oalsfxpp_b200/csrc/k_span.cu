@@ -8,15 +8,15 @@ bool launch_span_family(int kernel_id, const MixArgs& args, cudaStream_t st)
 {
 	static bool done[kKernelEnd] = {};
 	switch (kernel_id) {
-#define OALSFX_SX(id, CT, SL) \
-	case id: \
+#define OALSFX_SX(id, CT, SL, CHAIN) \
+	case id: { \
+		constexpr size_t bytes = static_cast<size_t>(span::shared_floats(CHAIN, SL)) * sizeof(float); \
 		if (!done[id]) { \
-			cudaFuncSetAttribute(span::span_reverb_kernel<CT, SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, span::shared_floats(CT, SL) * static_cast<int>(sizeof(float))); \
+			cudaFuncSetAttribute(span::span_kernel<CT, SL, CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)); \
 			done[id] = true; \
 		} \
-		span::span_reverb_kernel<CT, SL><<<static_cast<unsigned>(args.tile_count) * (kLanes / SL), span::kThreads, \
-			static_cast<size_t>(span::shared_floats(CT, SL)) * sizeof(float), st>>>(args); \
-		return true;
+		span::span_kernel<CT, SL, CHAIN><<<static_cast<unsigned>(args.tile_count) * (kLanes / SL), span::threads(CHAIN), bytes, st>>>(args); \
+		return true; }
 		OALSFX_SPAN_TABLE(OALSFX_SX)
 #undef OALSFX_SX
 	default: return false;

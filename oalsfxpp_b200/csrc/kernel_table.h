@@ -77,15 +77,19 @@
 	RX(kRelayMultiMonoHeavy, 1, true) \
 	RX(kRelayMultiStereoHeavy, 2, true)
 
-// Span kernels (span.cuh): the single-reverb-slot signature block-parallel in time.  SX(id, CT).
-// SX(id, CT, SL): SL = streams of a tile per CTA (a tile is shared by 32 / SL CTAs); ids of one CT are consecutive.
+// Span kernels (span.cuh): block-parallel in time.  SX(id, CT, SL, CHAIN): SL = streams of a tile per CTA (a tile is
+// shared by 32 / SL CTAs), CHAIN = the 4-slot equalizer + chorus + echo + reverb chain, else the single reverb slot;
+// the three ids of one signature are consecutive (SL = 32, 16, 8).
 #define OALSFX_SPAN_TABLE(SX) \
-	SX(kSpanReverbMono, 1, 32) \
-	SX(kSpanReverbMono16, 1, 16) \
-	SX(kSpanReverbMono8, 1, 8) \
-	SX(kSpanReverbStereo, 2, 32) \
-	SX(kSpanReverbStereo16, 2, 16) \
-	SX(kSpanReverbStereo8, 2, 8)
+	SX(kSpanReverbMono, 1, 32, false) \
+	SX(kSpanReverbMono16, 1, 16, false) \
+	SX(kSpanReverbMono8, 1, 8, false) \
+	SX(kSpanReverbStereo, 2, 32, false) \
+	SX(kSpanReverbStereo16, 2, 16, false) \
+	SX(kSpanReverbStereo8, 2, 8, false) \
+	SX(kSpanChainStereo, 2, 32, true) \
+	SX(kSpanChainStereo16, 2, 16, true) \
+	SX(kSpanChainStereo8, 2, 8, true)
 
 namespace oalsfx {
 
@@ -108,7 +112,7 @@ enum KernelId : int {
 	OALSFX_RELAY_TABLE(OALSFX_RX)
 	OALSFX_RELAY_MULTI_TABLE(OALSFX_RX)
 #undef OALSFX_RX
-#define OALSFX_SX(id, CT, SL) id,
+#define OALSFX_SX(id, CT, SL, CHAIN) id,
 	OALSFX_SPAN_TABLE(OALSFX_SX)
 #undef OALSFX_SX
 #define OALSFX_MX(id, CT, F0, F1, F2, F3, duo) id,
@@ -219,7 +223,7 @@ inline const char* kernel_name(int id)
 	OALSFX_RELAY_TABLE(OALSFX_RX)
 	OALSFX_RELAY_MULTI_TABLE(OALSFX_RX)
 #undef OALSFX_RX
-#define OALSFX_SX(sid, CT, SL) if (id == sid) return #sid;
+#define OALSFX_SX(sid, CT, SL, CHAIN) if (id == sid) return #sid;
 	OALSFX_SPAN_TABLE(OALSFX_SX)
 #undef OALSFX_SX
 #define OALSFX_MX(mid, CT, F0, F1, F2, F3, duo) if (id == mid) return #mid;

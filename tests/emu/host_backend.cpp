@@ -13,9 +13,12 @@
 
 #include "backend.h"
 #include "kernel_table.h"
+#include "span.cuh"
 
 namespace oalsfx {
 namespace {
+
+long long g_span_streams = 0; // streams x launches that took the span schedule (read by the tests)
 
 class HostBackend final : public Backend {
 public:
@@ -49,7 +52,9 @@ public:
 	}
 	// The device-only kernel families are emulated with the thread-per-stream bodies, so that the engine's selection
 	// logic, argument assembly and class tables are exercised on the CPU as well:
-	//   span   -> the plain single-reverb kernel (same values by construction, only the schedule differs on the GPU)
+	//   span   -> span::emulate_stream: the device kernel's own phase bodies, its three-stage software pipeline executed
+	//             serially in an adversarial order (any legal schedule must give the reference's values); streams off the
+	//             steady state run the exact thread-per-stream body, as on the device
 	//   relay  -> one exact single-effect pass per stage, in stage order, the running bus parked in dst
 	//             (the same additions in the same order; sanitized zero gains are simply skipped)
 	//   *multi -> tile by tile, the tile's class copied into the arguments as the kernels do in shared memory
@@ -112,9 +117,43 @@ public:
 			}
 			return true;
 		}
-#define OALSFX_SX(id, CT, SL) if (kernel_id == id) { kernel_id = (CT == 1 ? kReverbMono : kReverbStereo); }
+		int span_twin = -1;
+#define OALSFX_SX(id, CT, SL, CHAIN) if (kernel_id == id) { span_twin = (CHAIN ? kChainStereo : CT == 1 ? kReverbMono : kReverbStereo); }
 		OALSFX_SPAN_TABLE(OALSFX_SX)
 #undef OALSFX_SX
+		if (span_twin >= 0) {
+			for (int w = 0; w < a.tile_count; ++w) {
+				const int tile = a.tiles ? static_cast<int>(a.tiles[w].tile) : a.tile_first + w;
+				// the device decides per CTA (= per tile, or per share of a tile); per tile here
+				bool steady = true;
+				for (int lane = 0; lane < kLanes && steady; ++lane) {
+					if (tile * kLanes + lane < a.num_streams) {
+						steady = span_twin == kChainStereo ? span::Context<2, true>().setup(a, tile, lane) :
+							span_twin == kReverbMono ? span::Context<1, false>().setup(a, tile, lane) : span::Context<2, false>().setup(a, tile, lane);
+					}
+				}
+				for (int lane = 0; lane < kLanes; ++lane) {
+					if (tile * kLanes + lane >= a.num_streams) {
+						continue;
+					}
+					if (!steady) {
+						switch (span_twin) {
+						case kChainStereo: mix_stream<2, false, FxEqualizer, FxModDelay, FxEcho, FxReverb>(a, tile, lane); break;
+						case kReverbMono: mix_stream<1, false, FxReverb, FxNull, FxNull, FxNull>(a, tile, lane); break;
+						default: mix_stream<2, false, FxReverb, FxNull, FxNull, FxNull>(a, tile, lane); break;
+						}
+					} else {
+						++g_span_streams;
+						switch (span_twin) {
+						case kChainStereo: span::emulate_stream<2, true>(a, tile, lane); break;
+						case kReverbMono: span::emulate_stream<1, false>(a, tile, lane); break;
+						default: span::emulate_stream<2, false>(a, tile, lane); break;
+						}
+					}
+				}
+			}
+			return true;
+		}
 		if (kernel_id >= kKernelCount && kernel_id < kTabDry) { // a duo / quartet kernel: the CPU build runs its thread-per-stream twin
 			kernel_id = twin_of_fused(kernel_id);
 		}
@@ -204,6 +243,7 @@ private:
 } // namespace
 
 Backend* make_backend(int, std::string&) { return new HostBackend; }
+extern "C" long long oalsfx_emu_span_streams() { return g_span_streams; }
 const char* backend_build_info() { return "oalsfx host-emu (tests only)"; }
 
 } // namespace oalsfx

@@ -101,6 +101,7 @@ def emu_lib():
     if "emu" not in _CACHE:
         build_emu()
         _CACHE["emu"] = _eng.bind(C.CDLL(os.path.join(ROOT, "tests", "_build", "liboalsfx_emu.so")))
+        _CACHE["emu"].oalsfx_emu_span_streams.restype = C.c_longlong
     return _CACHE["emu"]
 
 

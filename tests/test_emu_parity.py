@@ -183,6 +183,21 @@ def test_span_selection_and_legality(checker, case, monkeypatch):
     _gpu_scenarios(monkeypatch).test_span_kernel_on_steady_state_blocks(checker, case)
 
 
+@pytest.mark.parametrize("case", ["default", "flanger-96k", "forest-short-echo", "short-first-blocks", "standard-reverb"])
+def test_span_chain_schedule_and_legality(checker, case, monkeypatch):
+    """The chain's span kernel: its phase bodies and its three-stage pipeline schedule (emulated serially in an
+    adversarial order by the CPU backend) against the checker, and that the schedule was really taken."""
+    before = H.emu_lib().oalsfx_emu_span_streams()
+    _gpu_scenarios(monkeypatch).test_span_chain_on_steady_state_blocks(checker, case)
+    assert H.emu_lib().oalsfx_emu_span_streams() > before
+
+
+def test_span_schedule_was_taken_for_the_single_reverb_slot(checker, monkeypatch):
+    before = H.emu_lib().oalsfx_emu_span_streams()
+    _gpu_scenarios(monkeypatch).test_span_kernel_on_steady_state_blocks(checker, "eax-stereo")
+    assert H.emu_lib().oalsfx_emu_span_streams() > before
+
+
 def test_class_per_tile_tables_chain(checker, monkeypatch):
     _gpu_scenarios(monkeypatch).test_class_per_tile_launch_many_presets(checker)
 

@@ -41,7 +41,12 @@ def _uses_device_sinf(script):
 def _assert_match(expect, got, exact, what=""):
     assert expect.shape == got.shape
     if exact:
-        assert np.array_equal(expect, got, equal_nan=True), (what, H.max_abs_diff(expect, got))
+        # bit for bit: the uint32 images must be equal (+0 / -0 and NaN payloads are NOT interchangeable)
+        e32 = np.ascontiguousarray(expect, dtype=np.float32).view(np.uint32)
+        g32 = np.ascontiguousarray(got, dtype=np.float32).view(np.uint32)
+        if not np.array_equal(e32, g32):
+            bad = np.argwhere(e32 != g32)
+            raise AssertionError((what, "first mismatch at", tuple(bad[0]), "count", len(bad), "max abs diff", H.max_abs_diff(expect, got)))
     else:
         finite = np.isfinite(expect)
         assert np.array_equal(finite, np.isfinite(got)), what
@@ -153,11 +158,12 @@ def test_cfg2_schedule_on_4096_streams(checker):
         _assert_match(expect, y[s], True, f"stream {s}")
 
 
-@pytest.mark.parametrize("family", ["quartet", "duo", "single", "relay"])
+@pytest.mark.parametrize("family", ["quartet", "duo", "single", "relay", "span"])
 def test_every_kernel_family_on_the_chain(checker, family, monkeypatch):
-    """The fused 4-slot stereo chain has four implementations (OALSFX_KERNEL, read when an engine is
-    created): the two-stage duo kernel (default), the four-stage quartet pipeline, the 4-lanes-per-stream
-    quad kernel and the plain thread-per-stream kernel.  Each must equal the checker bit for bit on a
+    """The fused 4-slot stereo chain has five implementations (OALSFX_KERNEL, read when an engine is
+    created): the two-stage duo kernel (default), the four-stage quartet pipeline, the relay pipeline, the plain
+    thread-per-stream kernel and -- on blocks without a pending update -- the time-parallel span kernel (here: the
+    device-side steady-state check and its exact fallback).  Each must equal the checker bit for bit on a
     schedule that exercises ramps (reverb gain), a tap cross-fade (reflections delay change in block 2),
     an equalizer step, a block size that is not a multiple of 4 and a partially filled last tile."""
     monkeypatch.setenv("OALSFX_KERNEL", family)
@@ -328,6 +334,82 @@ def test_span_kernel_on_steady_state_blocks(checker, case):
     for s in (0, 31, 32, 63, 64, S - 1):
         expect = H.run_script_orc(checker, fmt, rate, 1, script, x[s])
         _assert_match(expect, y[s], True, f"span {case} stream {s}")
+
+
+@pytest.mark.parametrize("case", ["default", "flanger-96k", "forest-short-echo", "short-first-blocks", "standard-reverb"])
+def test_span_chain_on_steady_state_blocks(checker, case):
+    """span.cuh on the 4-slot chain: blocks without a pending update run equalizer + chorus / flanger + echo + reverb
+    block-parallel in time as a three-stage software pipeline (phase A of span i+1, the recurrences of span i and
+    phase C of span i-1 overlap).  Steady-state blocks of odd sizes, a ragged last tile, parameter changes in between
+    (the update block and cross-fading blocks take the exact kernels), short echo / flanger delays (shorter spans or no
+    span at all), the standard reverb (no high-pass shelf)."""
+    lib = _lib()
+    rate = 96000 if case == "flanger-96k" else 48000
+    rtype = T.reverb if case == "standard-reverb" else T.eax_reverb
+    mtype = T.flanger if case == "flanger-96k" else T.chorus
+    chain = [T.equalizer, mtype, T.echo, rtype]
+    first = {3: ox.reverb_preset("Default", "forest", lib=lib), 2: ox.default_props(T.echo, lib=lib, delay_=0.002, lr_delay_=0.003)} if case == "forest-short-echo" else {}
+    if case == "flanger-96k":  # the default flanger sweeps its delay down to zero (depth 1): no span is legal with that
+        first = {1: ox.default_props(T.flanger, lib=lib, delay_=0.004, depth_=0.25, rate_=1.3, waveform_=0)}
+    second = {3: ox.default_props(rtype, lib=lib, gain_=0.5, decay_time_=3.0, reflections_delay_=0.02),
+              0: ox.default_props(T.equalizer, lib=lib, mid1_gain_=1.7, low_gain_=0.5),
+              2: ox.default_props(T.echo, lib=lib, delay_=0.05, feedback_=0.7)}
+    blocks = [50, 30, 70, 1024, 333] if case == "short-first-blocks" else [1024, 1024, 777, 64, 2, 1500, 1024, 31]
+    change_at = 4 if case != "short-first-blocks" else 99
+    S = 70
+    total = sum(blocks)
+    x = np.stack([H.noise(3000 + s, 2, total) for s in range(S)])
+    y = np.empty_like(x)
+    script = [("type", i, t) for i, t in enumerate(chain)] + [("props", i, p) for i, p in first.items()] + [("apply",)]
+    with ox.Engine(S, F.stereo, rate, 4, lib=lib) as eng:
+        for i, t in enumerate(chain):
+            eng.set_effect(i, t, first.get(i))
+        at = 0
+        for b, n in enumerate(blocks):
+            if b == change_at:
+                for i, p in second.items():
+                    eng.set_effect(i, chain[i], p)
+                    script += [("props", i, p)]
+                script += [("apply",)]
+            script += [("mix", n)]
+            y[:, at:at + n] = eng.mix(np.ascontiguousarray(x[:, at:at + n]))
+            at += n
+    for s in (0, 31, 32, 63, 64, S - 1):
+        expect = H.run_script_orc(checker, F.stereo, rate, 4, script, x[s])
+        _assert_match(expect, y[s], True, f"span chain {case} stream {s}")
+
+
+@pytest.mark.parametrize("tiles", [8, 50, 100])
+def test_span_chain_every_tile_share(checker, tiles):
+    """The chain's span kernel with a tile shared by 4 / 2 / 1 CTAs (8 / 16 / 32 streams per CTA)."""
+    import torch
+    lib = _lib()
+    S = tiles * 32
+    blocks = [256, 1024, 333, 1024]
+    total = sum(blocks)
+    chain = [T.equalizer, T.chorus, T.echo, T.eax_reverb]
+    base = [H.noise(7100 + s, 2, total) for s in range(4)]
+    dev = torch.device("cuda:0")
+    outs = []
+    with ox.Engine(S, F.stereo, 48000, 4, lib=lib) as eng:
+        for i, t in enumerate(chain):
+            eng.set_effect(i, t)
+        at = 0
+        for n in blocks:
+            xb = torch.from_numpy(np.stack([v[at:at + n] for v in base])).to(dev)
+            x = xb.repeat(S // 4, 1, 1).contiguous()
+            y = torch.empty_like(x)
+            eng.mix(x, y, frames=n, stream=torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            outs.append(y)
+            at += n
+    y = torch.cat(outs, dim=1)
+    per = y.view(S // 4, 4, total, 2)
+    assert bool((per == per[0:1]).all()), "streams with identical input diverged"
+    script = [("type", i, t) for i, t in enumerate(chain)] + [("apply",)] + [("mix", n) for n in blocks]
+    for k in range(4):
+        expect = H.run_script_orc(checker, F.stereo, 48000, 4, script, base[k])
+        _assert_match(expect, per[0, k].cpu().numpy(), True, f"span chain share, {tiles} tiles, input {k}")
 
 
 @pytest.mark.parametrize("tiles", [8, 50, 100])
