@@ -130,6 +130,7 @@ struct oalsfx_engine {
 	// 6 = as automatic (names the span kernel's tests).  OALSFX_KERNEL=auto|quartet|duo|single|relay|span overrides
 	// (A/B measurements and the parity tests of every family).
 	int family = 2;
+	int family_span_bulk = 1;           // OALSFX_SPAN_BULK=0: whole-tile spans stay on the load / store kernel; 2: whole tiles (and the bulk kernel) however few (A/B, tests)
 	// Host-buffer mix: tile slice the next launches are restricted to (0 = all tiles), and the
 	// engine-owned streams that overlap H2D, kernels and D2H of consecutive slices.
 	int slice_first = 0, slice_count = 0;
@@ -845,7 +846,15 @@ struct oalsfx_engine {
 			const bool span_chain = ki.id == kChainStereo;
 			if ((ki.id == kReverbMono || ki.id == kReverbStereo || span_chain) && whole_tiles && be->has_relay() && (family == 2 || family == 6) &&
 				a.update_mask == 0 && a.tile_count <= kSpanMaxTiles && slice_count == 0 && frames_since_update >= 128) {
-				const int share = a.tile_count * 4 <= 148 ? 2 : a.tile_count * 2 <= 148 ? 1 : 0;
+				const int share = family_span_bulk == 2 ? 0 : a.tile_count * 4 <= 148 ? 2 : a.tile_count * 2 <= 148 ? 1 : 0;
+				// whole tiles per CTA: the ring traffic as bulk copies (span_bulk_kernel) if its timing is legal for this preset
+				if (share == 0 && family_span_bulk) {
+					const int tb = span::plan_bulk_frames(a, span_chain);
+					if (tb > 0) {
+						a.span_frames = tb;
+						return be->launch_mix(span_chain ? kSpanBulkChainStereo : ki.id == kReverbMono ? kSpanBulkReverbMono : kSpanBulkReverbStereo, a, stream);
+					}
+				}
 				const int t = span::plan_frames(a, span_chain, kLanes >> share);
 				if (t > 0) {
 					a.span_frames = t;
@@ -942,6 +951,9 @@ int oalsfx_engine_create(const oalsfx_engine_desc* desc, oalsfx_engine** out)
 	e->slots = desc->effect_count;
 	if (const char* fam = std::getenv("OALSFX_KERNEL")) {
 		e->family = (std::strcmp(fam, "single") == 0 ? 0 : std::strcmp(fam, "quartet") == 0 ? 3 : std::strcmp(fam, "duo") == 0 ? 4 : std::strcmp(fam, "relay") == 0 ? 5 : std::strcmp(fam, "span") == 0 ? 6 : 2);
+	}
+	if (const char* sb = std::getenv("OALSFX_SPAN_BULK")) {
+		e->family_span_bulk = std::atoi(sb);
 	}
 	e->be = make_backend(desc->device, g_create_error);
 	if (!e->be) {

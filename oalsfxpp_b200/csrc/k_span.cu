@@ -19,6 +19,17 @@ bool launch_span_family(int kernel_id, const MixArgs& args, cudaStream_t st)
 		return true; }
 		OALSFX_SPAN_TABLE(OALSFX_SX)
 #undef OALSFX_SX
+#define OALSFX_BX(id, CT, CHAIN) \
+	case id: { \
+		constexpr size_t bytes = static_cast<size_t>(span::bulk_shared_floats(CHAIN)) * sizeof(float); \
+		if (!done[id]) { \
+			cudaFuncSetAttribute(span::span_bulk_kernel<CT, CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)); \
+			done[id] = true; \
+		} \
+		span::span_bulk_kernel<CT, CHAIN><<<static_cast<unsigned>(args.tile_count), span::threads(CHAIN), bytes, st>>>(args); \
+		return true; }
+		OALSFX_SPAN_BULK_TABLE(OALSFX_BX)
+#undef OALSFX_BX
 	default: return false;
 	}
 }

@@ -91,6 +91,12 @@
 	SX(kSpanChainStereo16, 2, 16, true) \
 	SX(kSpanChainStereo8, 2, 8, true)
 
+// The same with bulk-asynchronous ring traffic, whole tiles only (span_bulk_kernel).  BX(id, CT, CHAIN).
+#define OALSFX_SPAN_BULK_TABLE(BX) \
+	BX(kSpanBulkReverbMono, 1, false) \
+	BX(kSpanBulkReverbStereo, 2, false) \
+	BX(kSpanBulkChainStereo, 2, true)
+
 namespace oalsfx {
 
 enum KernelId : int {
@@ -115,6 +121,9 @@ enum KernelId : int {
 #define OALSFX_SX(id, CT, SL, CHAIN) id,
 	OALSFX_SPAN_TABLE(OALSFX_SX)
 #undef OALSFX_SX
+#define OALSFX_BX(id, CT, CHAIN) id,
+	OALSFX_SPAN_BULK_TABLE(OALSFX_BX)
+#undef OALSFX_BX
 #define OALSFX_MX(id, CT, F0, F1, F2, F3, duo) id,
 	OALSFX_MULTI_TABLE(OALSFX_MX)
 #undef OALSFX_MX
@@ -226,6 +235,9 @@ inline const char* kernel_name(int id)
 #define OALSFX_SX(sid, CT, SL, CHAIN) if (id == sid) return #sid;
 	OALSFX_SPAN_TABLE(OALSFX_SX)
 #undef OALSFX_SX
+#define OALSFX_BX(bid, CT, CHAIN) if (id == bid) return #bid;
+	OALSFX_SPAN_BULK_TABLE(OALSFX_BX)
+#undef OALSFX_BX
 #define OALSFX_MX(mid, CT, F0, F1, F2, F3, duo) if (id == mid) return #mid;
 	OALSFX_MULTI_TABLE(OALSFX_MX)
 #undef OALSFX_MX

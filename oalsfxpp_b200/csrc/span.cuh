@@ -50,7 +50,7 @@ namespace span {
 
 constexpr int kParallelWarps = 8;
 constexpr int kBuffers = 3;               // spans in flight: A(i+1), B(i), C(i-1)
-OALSFX_CX int serial_warps(bool chain) { return chain ? 6 : 4; }
+OALSFX_CX int serial_warps(bool chain) { return chain ? 4 : 2; }
 OALSFX_CX int threads(bool chain) { return (kParallelWarps + serial_warps(chain)) * kLanes; }
 OALSFX_CX int staged_words(bool chain) { return chain ? 12 : 8; }
 // frames a staging buffer holds (= the longest span) for SL streams per CTA
@@ -97,7 +97,17 @@ struct Legality {
 	}
 };
 
-inline bool reverb_legal(const ReverbCoef& c, int t)
+// When the ring accesses of a span's phases take effect, as iteration offsets from the span index:
+//   ra / rc  reads of phase A / C,   wb / wc  writes of phase B / C,   mr / mw  the chorus ring's reads / writes
+// span_kernel (loads and stores at the point of use):       A one iteration before B, C one after
+// span_bulk_kernel (bulk copies issued ahead, stores behind): A's rows fetched two iterations before B, C's in B's own
+//   iteration; B's stores land one iteration after B, C's two; the chorus taps are requested one iteration before C
+struct Timing { int ra, rc, wb, wc, mr, mw; };
+constexpr Timing kDirectTiming = {kPhA, kPhC, kPhB, kPhC, kPhC, kPhC};
+constexpr Timing kBulkTiming = {-2, 0, 1, 2, 0, 1};
+constexpr int kBulkFrames = 16;           // span length of span_bulk_kernel (shared memory holds every ring row of a span)
+
+inline bool reverb_legal(const ReverbCoef& c, int t, const Timing& tm = kDirectTiming)
 {
 	if (c.mod_depth != 0.0F) {
 		return false;
@@ -107,20 +117,20 @@ inline bool reverb_legal(const ReverbCoef& c, int t)
 	const int len0 = c.mask[0] + 1;
 	for (int l = 0; l < 4; ++l) {
 		// main line: shelves write at the position (B), the early scatter feeds it late_feed_tap behind (C)
-		g.pair(kPhC, c.early_tap[l], kPhB, 0, len0, true);
-		g.pair(kPhC, c.early_tap[l], kPhC, c.late_feed_tap, len0, false);
-		g.pair(kPhA, c.late_tap[l], kPhB, 0, len0, true);
-		g.pair(kPhA, c.late_tap[l], kPhC, c.late_feed_tap, len0, true);
-		g.pair(kPhC, c.early_ap_off[l], kPhC, 0, c.mask[1] + 1, false);
-		g.pair(kPhC, c.early_off[l], kPhC, 0, c.mask[2] + 1, true);
-		g.pair(kPhC, c.late_ap_off[l], kPhC, 0, c.mask[3] + 1, false);
-		g.pair(kPhA, c.late_off[l], kPhC, 0, c.mask[4] + 1, true);
+		g.pair(tm.rc, c.early_tap[l], tm.wb, 0, len0, true);
+		g.pair(tm.rc, c.early_tap[l], tm.wc, c.late_feed_tap, len0, false);
+		g.pair(tm.ra, c.late_tap[l], tm.wb, 0, len0, true);
+		g.pair(tm.ra, c.late_tap[l], tm.wc, c.late_feed_tap, len0, true);
+		g.pair(tm.rc, c.early_ap_off[l], tm.wc, 0, c.mask[1] + 1, false);
+		g.pair(tm.rc, c.early_off[l], tm.wc, 0, c.mask[2] + 1, true);
+		g.pair(tm.rc, c.late_ap_off[l], tm.wc, 0, c.mask[3] + 1, false);
+		g.pair(tm.ra, c.late_off[l], tm.wc, 0, c.mask[4] + 1, true);
 	}
-	g.writers(kPhB, 0, kPhC, c.late_feed_tap, len0);
+	g.writers(tm.wb, 0, tm.wc, c.late_feed_tap, len0);
 	return g.ok;
 }
 
-inline bool mod_delay_legal(const ModDelayCoef& c, int t)
+inline bool mod_delay_legal(const ModDelayCoef& c, int t, const Timing& tm = kDirectTiming)
 {
 	Legality g;
 	g.t = t;
@@ -129,18 +139,18 @@ inline bool mod_delay_legal(const ModDelayCoef& c, int t)
 	if (dmin < 1 || c.lfo_range <= kMaxBlockFrames) {
 		return false;
 	}
-	g.pair(kPhC, dmin, kPhC, 0, c.mask + 1, false);
-	g.pair(kPhC, dmax, kPhC, 0, c.mask + 1, false);
+	g.pair(tm.mr, dmin, tm.mw, 0, c.mask + 1, false);
+	g.pair(tm.mr, dmax, tm.mw, 0, c.mask + 1, false);
 	return g.ok && dmax < c.mask + 1;
 }
 
-inline bool echo_legal(const EchoCoef& c, int t)
+inline bool echo_legal(const EchoCoef& c, int t, const Timing& tm = kDirectTiming)
 {
 	Legality g;
 	g.t = t;
-	g.pair(kPhC, c.tap1, kPhB, 0, c.mask + 1, false);
-	g.pair(kPhC, c.tap2, kPhB, 0, c.mask + 1, false);
-	g.pair(kPhA, c.tap2, kPhB, 0, c.mask + 1, false);
+	g.pair(tm.rc, c.tap1, tm.wb, 0, c.mask + 1, false);
+	g.pair(tm.rc, c.tap2, tm.wb, 0, c.mask + 1, false);
+	g.pair(tm.ra, c.tap2, tm.wb, 0, c.mask + 1, false);
 	return g.ok;
 }
 
@@ -158,6 +168,16 @@ inline int plan_frames(const MixArgs& a, bool chain, int stream_lanes)
 		}
 	}
 	return 0;
+}
+
+// span_bulk_kernel's fixed span length if its timing is legal for these coefficient blocks, or 0.
+inline int plan_bulk_frames(const MixArgs& a, bool chain)
+{
+	bool ok = reverb_legal(a.slot[chain ? 3 : 0].u.reverb, kBulkFrames, kBulkTiming);
+	if (chain) {
+		ok = ok && mod_delay_legal(a.slot[1].u.mod_delay, kBulkFrames, kBulkTiming) && echo_legal(a.slot[2].u.echo, kBulkFrames, kBulkTiming);
+	}
+	return ok ? kBulkFrames : 0;
 }
 
 // ---- staging buffers -------------------------------------------------------------------------------------------
@@ -205,6 +225,51 @@ OALSFX_HD void encode_wet(const SendCoef& sc, const float* x, float* wet)
 	}
 }
 
+// ---- where the ring stores of phases B and C go ------------------------------------------------------------------------
+// Rows of phase C (each = one ring line): early all-pass 0..3, early line 4..7, main line feed 8..11 (late_feed_tap
+// behind the position), late all-pass 12..15, late line 16..19.  Rows of phase B: main line 0..3, echo ring 4.
+constexpr int kOutEap = 0, kOutEline = 4, kOutFeed = 8, kOutLap = 12, kOutLline = 16, kOutRowsC = 20;
+constexpr int kOutMain = 0, kOutEcho = 4, kOutRowsB = 5;
+
+// straight to the rings
+struct RingSinkC {
+	const ReverbCoef& c;
+	LaneMem ring;
+	int pos;
+	OALSFX_HD void put(int row, float v) const
+	{
+		const int l = row & 3;
+		const int r = row < kOutEline ? 1 : row < kOutFeed ? 2 : row < kOutLap ? 0 : row < kOutLline ? 3 : 4;
+		const int at = (row >= kOutFeed && row < kOutLap) ? pos - c.late_feed_tap : pos;
+		ring.st(c.ring_base[r] + l * (c.mask[r] + 1) + (at & c.mask[r]), v);
+	}
+};
+struct RingSinkB {
+	const ReverbCoef& c;
+	LaneMem ring_rev, ring_echo;
+	int echo_mask;
+	int rev_pos0, echo_pos0;      // ring positions of the span's first frame
+	OALSFX_HD void put(int row, int t, float v) const
+	{
+		if (row < kOutEcho) {
+			ring_rev.st(c.ring_base[0] + row * (c.mask[0] + 1) + ((rev_pos0 + t) & c.mask[0]), v);
+		} else {
+			ring_echo.st((echo_pos0 + t) & echo_mask, v);
+		}
+	}
+};
+// into shared-memory row buffers [row][frame][lane] that bulk copies move to the rings (span_bulk_kernel)
+template <int T>
+struct StageSinkC {
+	float* base;                  // + frame * 32 + lane
+	OALSFX_HD void put(int row, float v) const { base[row * (T * kLanes)] = v; }
+};
+template <int T>
+struct StageSinkB {
+	float* base;                  // + lane
+	OALSFX_HD void put(int row, int t, float v) const { base[(row * T + t) * kLanes] = v; }
+};
+
 // ---- per-stream context ------------------------------------------------------------------------------------------
 template <int CT, bool CHAIN>
 struct Context {
@@ -213,10 +278,10 @@ struct Context {
 	const float* src;
 	float* dst;
 	bool io_ok;
-	LaneMem ring_rev, ring_mod, ring_echo;
-	uint32_t *st_rev, *st_eq, *st_mod, *st_echo, *ss;
-	int32_t rev_off, mod_off, echo_off;       // ring offsets at the start of the block
-	int32_t mod_ph[2];                        // chorus LFO phases at the start of the block
+	LaneMem ring_rev = {nullptr}, ring_mod = {nullptr}, ring_echo = {nullptr};
+	uint32_t *st_rev = nullptr, *st_eq = nullptr, *st_mod = nullptr, *st_echo = nullptr, *ss = nullptr;
+	int32_t rev_off = 0, mod_off = 0, echo_off = 0;  // ring offsets at the start of the block
+	int32_t mod_ph[2] = {0, 0};               // chorus LFO phases at the start of the block
 	float gain[8][CT];                        // the reverb's pan gains, inaudible ones as exact zeros
 
 	// Loads the per-stream state the phases need; returns whether the stream is in the steady state.
@@ -338,9 +403,10 @@ struct Context {
 	}
 
 	// ---- phase C ----
-	struct TapsC { float early[4], eap[4], eline[4], lap[4], mod[2], echo[2]; int32_t mod_pos; };
+	struct TapsC { float early[4], eap[4], eline[4], lap[4], echo[2]; };
+	struct TapsMod { float v[2]; int32_t pos; };
 
-	OALSFX_HD void load_c(const MixArgs& a, int n, TapsC& k) const
+	OALSFX_HD void load_c(const MixArgs& a, int n, TapsC& k, TapsMod& md) const
 	{
 		const ReverbCoef& c = a.slot[RP].u.reverb;
 		const int pos = rev_off + n;
@@ -353,26 +419,63 @@ struct Context {
 			k.lap[l] = ring_ld(ring_rev, c.ring_base[3] + l * lap_len + ((pos - c.late_ap_off[l]) & c.mask[3]));
 		}
 		if (CHAIN) {
-			const ModDelayCoef& m = a.slot[1].u.mod_delay;
-			const int32_t mlen = m.mask + 1;
-			k.mod_pos = mod_off + n;
-			OALSFX_UNROLL
-			for (int side = 0; side < 2; ++side) {
-				int32_t ph = mod_ph[side] + n;         // n <= 2048 < lfo_range (host-checked): at most one wrap
-				ph = (ph >= m.lfo_range ? ph - m.lfo_range : ph);
-				const int32_t d = FxModDelay::lfo_delay(m, ph);
-				k.mod[side] = ring_ld(ring_mod, side * mlen + ((k.mod_pos - d) & m.mask));
-			}
+			load_mod(a, n, md);
 			const EchoCoef& e = a.slot[2].u.echo;
 			k.echo[0] = ring_ld(ring_echo, (echo_off + n - e.tap1) & e.mask);
 			k.echo[1] = ring_ld(ring_echo, (echo_off + n - e.tap2) & e.mask);
 		}
 	}
 
-	// vector_allpass_x with the taps already read (FxReverbT::vector_allpass2, fx_reverb.cuh)
-	OALSFX_HD void allpass(const ReverbCoef& c, F2& va, F2& vb, const float* tp, int ring_idx, int pos) const
+	// the chorus / flanger taps: LFO-modulated positions, always read in place
+	OALSFX_HD void load_mod(const MixArgs& a, int n, TapsMod& k) const
 	{
-		const int len = c.mask[ring_idx] + 1, word0 = c.ring_base[ring_idx], mask = c.mask[ring_idx];
+		const ModDelayCoef& m = a.slot[1].u.mod_delay;
+		const int32_t mlen = m.mask + 1;
+		k.pos = mod_off + n;
+		OALSFX_UNROLL
+		for (int side = 0; side < 2; ++side) {
+			int32_t ph = mod_ph[side] + n;         // n <= 2048 < lfo_range (host-checked): at most one wrap
+			ph = (ph >= m.lfo_range ? ph - m.lfo_range : ph);
+			const int32_t d = FxModDelay::lfo_delay(m, ph);
+			k.v[side] = ring_ld(ring_mod, side * mlen + ((k.pos - d) & m.mask));
+		}
+	}
+
+	// Taps from row buffers [row][frame][LANES] filled by bulk copies (span_bulk_kernel); `rows` points at this
+	// thread's element of row 0.  Row order: see tap_row_a / tap_row_c.
+	template <int T, int LANES>
+	OALSFX_HD void fetch_a(const float* rows, TapsA& k) const
+	{
+		OALSFX_UNROLL
+		for (int l = 0; l < 4; ++l) {
+			k.late[l] = rows[(0 + l) * (T * LANES)];
+			k.lline[l] = rows[(4 + l) * (T * LANES)];
+		}
+		if (CHAIN) {
+			k.echo2 = rows[8 * (T * LANES)];
+		}
+	}
+	template <int T, int LANES>
+	OALSFX_HD void fetch_c(const float* rows, TapsC& k) const
+	{
+		OALSFX_UNROLL
+		for (int l = 0; l < 4; ++l) {
+			k.early[l] = rows[(0 + l) * (T * LANES)];
+			k.eap[l] = rows[(4 + l) * (T * LANES)];
+			k.eline[l] = rows[(8 + l) * (T * LANES)];
+			k.lap[l] = rows[(12 + l) * (T * LANES)];
+		}
+		if (CHAIN) {
+			k.echo[0] = rows[16 * (T * LANES)];
+			k.echo[1] = rows[17 * (T * LANES)];
+		}
+	}
+
+	// vector_allpass_x with the taps already read (FxReverbT::vector_allpass2, fx_reverb.cuh); the four ring
+	// stores go to rows row0 .. row0 + 3 of the sink
+	template <class Sink>
+	OALSFX_HD static void allpass(const ReverbCoef& c, F2& va, F2& vb, const float* tp, const Sink& out, int row0)
+	{
 		const F2 ta = f2(tp[0], tp[1]), tb = f2(tp[2], tp[3]);
 		const F2 ina = va, inb = vb;
 		va = ta - (ina * c.ap_feed_coeff);
@@ -380,14 +483,14 @@ struct Context {
 		F2 fa = ina + (va * c.ap_feed_coeff);
 		F2 fb = inb + (vb * c.ap_feed_coeff);
 		R::scatter2(fa, fb, c.mix_x, c.mix_y);
-		ring_rev.st(word0 + 0 * len + (pos & mask), f2_lo(fa));
-		ring_rev.st(word0 + 1 * len + (pos & mask), f2_hi(fa));
-		ring_rev.st(word0 + 2 * len + (pos & mask), f2_lo(fb));
-		ring_rev.st(word0 + 3 * len + (pos & mask), f2_hi(fb));
+		out.put(row0 + 0, f2_lo(fa));
+		out.put(row0 + 1, f2_hi(fa));
+		out.put(row0 + 2, f2_lo(fb));
+		out.put(row0 + 3, f2_hi(fb));
 	}
 
-	template <class S>
-	OALSFX_HD void phase_c(const MixArgs& a, const S& sg, int buf, int t, int n, const float* x, const TapsC& k) const
+	template <class S, class Sink>
+	OALSFX_HD void phase_c(const MixArgs& a, const S& sg, int buf, int t, int n, const float* x, const TapsC& k, const TapsMod& md, const Sink& out) const
 	{
 		const ReverbCoef& c = a.slot[RP].u.reverb;
 		float acc[CT];
@@ -413,11 +516,11 @@ struct Context {
 				const ModDelayCoef& m = a.slot[1].u.mod_delay;
 				float wet[kWetChannels];
 				encode_wet<CT>(a.aux[1], x, wet);
-				const int32_t mlen = m.mask + 1, mpos = k.mod_pos & m.mask;
+				const int32_t mlen = m.mask + 1, mpos = md.pos & m.mask;
 				float tt[2];
 				OALSFX_UNROLL
 				for (int side = 0; side < 2; ++side) {
-					tt[side] = k.mod[side] * m.feedback;
+					tt[side] = md.v[side] * m.feedback;
 					ring_mod.st(side * mlen + mpos, wet[0] + tt[side]);
 				}
 				if (CT == 2) {
@@ -446,19 +549,15 @@ struct Context {
 				}
 			}
 		}
-		const int pos = rev_off + n;
-		const int main_len = c.mask[0] + 1, main0 = c.ring_base[0], main_mask = c.mask[0];
-		const int eline_len = c.mask[2] + 1, eline0 = c.ring_base[2], eline_mask = c.mask[2];
-		const int lline_len = c.mask[4] + 1, lline0 = c.ring_base[4], lline_mask = c.mask[4];
 		float out8[8];
 		// early reflections (the EARLY half of FxReverbT::body)
 		F2 fa = f2(k.early[0], k.early[1]) * f2(c.early_tap_coeff[0], c.early_tap_coeff[1]);
 		F2 fb = f2(k.early[2], k.early[3]) * f2(c.early_tap_coeff[2], c.early_tap_coeff[3]);
-		allpass(c, fa, fb, k.eap, 1, pos);
-		ring_rev.st(eline0 + 0 * eline_len + (pos & eline_mask), f2_hi(fb));
-		ring_rev.st(eline0 + 1 * eline_len + (pos & eline_mask), f2_lo(fb));
-		ring_rev.st(eline0 + 2 * eline_len + (pos & eline_mask), f2_hi(fa));
-		ring_rev.st(eline0 + 3 * eline_len + (pos & eline_mask), f2_lo(fa));
+		allpass(c, fa, fb, k.eap, out, kOutEap);
+		out.put(kOutEline + 0, f2_hi(fb));   // delay_line_in4_rev: line j receives f[3 - j]
+		out.put(kOutEline + 1, f2_lo(fb));
+		out.put(kOutEline + 2, f2_hi(fa));
+		out.put(kOutEline + 3, f2_lo(fa));
 		fa = fa + (f2(k.eline[0], k.eline[1]) * f2(c.early_coeff[0], c.early_coeff[1]));
 		fb = fb + (f2(k.eline[2], k.eline[3]) * f2(c.early_coeff[2], c.early_coeff[3]));
 		out8[0] = f2_lo(fa);
@@ -468,16 +567,15 @@ struct Context {
 		{
 			F2 ra = fa, rb = fb;
 			R::scatter2_reversed(ra, rb, c.mix_x, c.mix_y);
-			const int feed = (pos - c.late_feed_tap) & main_mask;
-			ring_rev.st(main0 + 0 * main_len + feed, f2_hi(rb));
-			ring_rev.st(main0 + 1 * main_len + feed, f2_lo(rb));
-			ring_rev.st(main0 + 2 * main_len + feed, f2_hi(ra));
-			ring_rev.st(main0 + 3 * main_len + feed, f2_lo(ra));
+			out.put(kOutFeed + 0, f2_hi(rb));    // main line, late_feed_tap behind the position
+			out.put(kOutFeed + 1, f2_lo(rb));
+			out.put(kOutFeed + 2, f2_hi(ra));
+			out.put(kOutFeed + 3, f2_lo(ra));
 		}
 		// late reverb after the T60 filters
 		fa = f2(sg.at(buf, kWL + 0, t), sg.at(buf, kWL + 1, t));
 		fb = f2(sg.at(buf, kWL + 2, t), sg.at(buf, kWL + 3, t));
-		allpass(c, fa, fb, k.lap, 3, pos);
+		allpass(c, fa, fb, k.lap, out, kOutLap);
 		out8[4] = f2_lo(fa);
 		out8[5] = f2_hi(fa);
 		out8[6] = f2_lo(fb);
@@ -485,10 +583,10 @@ struct Context {
 		{
 			F2 ra = fa, rb = fb;
 			R::scatter2_reversed(ra, rb, c.mix_x, c.mix_y);
-			ring_rev.st(lline0 + 0 * lline_len + (pos & lline_mask), f2_hi(rb));
-			ring_rev.st(lline0 + 1 * lline_len + (pos & lline_mask), f2_lo(rb));
-			ring_rev.st(lline0 + 2 * lline_len + (pos & lline_mask), f2_hi(ra));
-			ring_rev.st(lline0 + 3 * lline_len + (pos & lline_mask), f2_lo(ra));
+			out.put(kOutLline + 0, f2_hi(rb));
+			out.put(kOutLline + 1, f2_lo(rb));
+			out.put(kOutLline + 2, f2_hi(ra));
+			out.put(kOutLline + 3, f2_lo(ra));
 		}
 		// pan with static gains (oalsfxpp.cpp:6142-6166, 2752-2798): inaudible gains are exact zeros here
 		OALSFX_UNROLL
@@ -569,80 +667,104 @@ struct Biquad2 {
 	}
 };
 
-// Master shelves of reverb lines (2p, 2p+1) -> main delay line (reverb_input_stage, fx_reverb.cuh).
-struct ShelfPair {
+// Master shelves of reverb lines as packed pairs (2p, 2p + 1) -> main delay line (reverb_input_stage, fx_reverb.cuh).
+// NPAIR = 2: one thread runs both pairs (a whole tile per CTA: every lane has a stream); NPAIR = 1: pair p0 only (a tile
+// shared by several CTAs: the lanes that would idle take the second pair -- same instructions, half as many per step).
+template <int NPAIR>
+struct Shelves {
 	using R = FxReverbTail;
-	Biquad2 lp, hp;
-	OALSFX_HD void load(const uint32_t* st, int p)
+	Biquad2 lp[NPAIR], hp[NPAIR];
+	OALSFX_HD void load(const uint32_t* st, int p0)
 	{
-		lp.load(st + (R::kWLp + (2 * p) * 4) * kLanes, st + (R::kWLp + (2 * p + 1) * 4) * kLanes);
-		hp.load(st + (R::kWHp + (2 * p) * 4) * kLanes, st + (R::kWHp + (2 * p + 1) * 4) * kLanes);
+		OALSFX_UNROLL
+		for (int i = 0; i < NPAIR; ++i) {
+			const int p = p0 + i;
+			lp[i].load(st + (R::kWLp + (2 * p) * 4) * kLanes, st + (R::kWLp + (2 * p + 1) * 4) * kLanes);
+			hp[i].load(st + (R::kWHp + (2 * p) * 4) * kLanes, st + (R::kWHp + (2 * p + 1) * 4) * kLanes);
+		}
 	}
-	OALSFX_HD void store(uint32_t* st, int p) const
+	OALSFX_HD void store(uint32_t* st, int p0) const
 	{
-		lp.store(st + (R::kWLp + (2 * p) * 4) * kLanes, st + (R::kWLp + (2 * p + 1) * 4) * kLanes);
-		hp.store(st + (R::kWHp + (2 * p) * 4) * kLanes, st + (R::kWHp + (2 * p + 1) * 4) * kLanes);
+		OALSFX_UNROLL
+		for (int i = 0; i < NPAIR; ++i) {
+			const int p = p0 + i;
+			lp[i].store(st + (R::kWLp + (2 * p) * 4) * kLanes, st + (R::kWLp + (2 * p + 1) * 4) * kLanes);
+			hp[i].store(st + (R::kWHp + (2 * p) * 4) * kLanes, st + (R::kWHp + (2 * p + 1) * 4) * kLanes);
+		}
 	}
-	template <class S>
-	OALSFX_HD void run(const ReverbCoef& c, const S& sg, int buf, int count, const LaneMem& ring, int pos0, int p)
+	template <class S, class Sink>
+	OALSFX_HD void run(const ReverbCoef& c, const S& sg, int buf, int count, const Sink& out, int p0)
 	{
-		const int main_len = c.mask[0] + 1, main0 = c.ring_base[0], main_mask = c.mask[0];
 #if defined(__CUDA_ARCH__)
-#pragma unroll 4
+#pragma unroll 2
 #endif
 		for (int t = 0; t < count; ++t) {
-			F2 v = f2(sg.at(buf, kWA + 2 * p, t), sg.at(buf, kWA + 2 * p + 1, t));
-			v = lp.step(c.lp, v);
-			if (c.is_eax) {
-				v = hp.step(c.hp, v);
+			OALSFX_UNROLL
+			for (int i = 0; i < NPAIR; ++i) {
+				const int p = p0 + i;
+				F2 v = f2(sg.at(buf, kWA + 2 * p, t), sg.at(buf, kWA + 2 * p + 1, t));
+				v = lp[i].step(c.lp, v);
+				if (c.is_eax) {
+					v = hp[i].step(c.hp, v);
+				}
+				out.put(kOutMain + 2 * p, t, f2_lo(v));
+				out.put(kOutMain + 2 * p + 1, t, f2_hi(v));
 			}
-			const int at = (pos0 + t) & main_mask;
-			ring.st(main0 + (2 * p) * main_len + at, f2_lo(v));
-			ring.st(main0 + (2 * p + 1) * main_len + at, f2_hi(v));
 		}
 	}
 };
 
-// late_t60_filter of lines (2h, 2h+1), in place (oalsfxpp.cpp:7691-7719; FxReverbT::body).
-struct T60Pair {
+// late_t60_filter of reverb lines as packed pairs, in place (oalsfxpp.cpp:7691-7719; FxReverbT::body).  NPAIR as above.
+template <int NPAIR>
+struct T60s {
 	using R = FxReverbTail;
-	F2 p[2][2];
-	OALSFX_HD void load(const uint32_t* st, int h)
+	F2 p[NPAIR][2][2];   // [pair][section][x1 / y1]
+	OALSFX_HD void load(const uint32_t* st, int p0)
 	{
 		OALSFX_UNROLL
-		for (int q = 0; q < 4; ++q) {
-			p[q >> 1][q & 1] = f2(word_as_float(st[(R::kWT60 + (2 * h) * 4 + q) * kLanes]), word_as_float(st[(R::kWT60 + (2 * h + 1) * 4 + q) * kLanes]));
+		for (int i = 0; i < NPAIR; ++i) {
+			const int h = p0 + i;
+			OALSFX_UNROLL
+			for (int q = 0; q < 4; ++q) {
+				p[i][q >> 1][q & 1] = f2(word_as_float(st[(R::kWT60 + (2 * h) * 4 + q) * kLanes]), word_as_float(st[(R::kWT60 + (2 * h + 1) * 4 + q) * kLanes]));
+			}
 		}
 	}
-	OALSFX_HD void store(uint32_t* st, int h) const
+	OALSFX_HD void store(uint32_t* st, int p0) const
 	{
 		OALSFX_UNROLL
-		for (int q = 0; q < 4; ++q) {
-			st[(R::kWT60 + (2 * h) * 4 + q) * kLanes] = float_as_word(f2_lo(p[q >> 1][q & 1]));
-			st[(R::kWT60 + (2 * h + 1) * 4 + q) * kLanes] = float_as_word(f2_hi(p[q >> 1][q & 1]));
+		for (int i = 0; i < NPAIR; ++i) {
+			const int h = p0 + i;
+			OALSFX_UNROLL
+			for (int q = 0; q < 4; ++q) {
+				st[(R::kWT60 + (2 * h) * 4 + q) * kLanes] = float_as_word(f2_lo(p[i][q >> 1][q & 1]));
+				st[(R::kWT60 + (2 * h + 1) * 4 + q) * kLanes] = float_as_word(f2_hi(p[i][q >> 1][q & 1]));
+			}
 		}
 	}
 	template <class S>
-	OALSFX_HD void run(const ReverbCoef& c, const S& sg, int buf, int count, int h)
+	OALSFX_HD void run(const ReverbCoef& c, const S& sg, int buf, int count, int p0)
 	{
-		const int j = 2 * h;
-		const F2 lf0 = f2(c.t60_lf[j][0], c.t60_lf[j + 1][0]), lf1 = f2(c.t60_lf[j][1], c.t60_lf[j + 1][1]), lf2 = f2(c.t60_lf[j][2], c.t60_lf[j + 1][2]);
-		const F2 hf0 = f2(c.t60_hf[j][0], c.t60_hf[j + 1][0]), hf1 = f2(c.t60_hf[j][1], c.t60_hf[j + 1][1]), hf2 = f2(c.t60_hf[j][2], c.t60_hf[j + 1][2]);
-		const F2 mid = f2(c.t60_mid[j], c.t60_mid[j + 1]);
 #if defined(__CUDA_ARCH__)
-#pragma unroll 4
+#pragma unroll 2
 #endif
 		for (int t = 0; t < count; ++t) {
-			const F2 in = f2(sg.at(buf, kWL + j, t), sg.at(buf, kWL + j + 1, t));
-			const F2 o1 = (lf0 * in) + (lf1 * p[0][0]) + (lf2 * p[0][1]);
-			p[0][0] = in;
-			p[0][1] = o1;
-			const F2 o2 = (hf0 * o1) + (hf1 * p[1][0]) + (hf2 * p[1][1]);
-			p[1][0] = o1;
-			p[1][1] = o2;
-			const F2 out = mid * o2;
-			sg.at(buf, kWL + j, t) = f2_lo(out);
-			sg.at(buf, kWL + j + 1, t) = f2_hi(out);
+			OALSFX_UNROLL
+			for (int i = 0; i < NPAIR; ++i) {
+				const int j = 2 * (p0 + i);
+				const F2 in = f2(sg.at(buf, kWL + j, t), sg.at(buf, kWL + j + 1, t));
+				const F2 o1 = (f2(c.t60_lf[j][0], c.t60_lf[j + 1][0]) * in) + (f2(c.t60_lf[j][1], c.t60_lf[j + 1][1]) * p[i][0][0]) +
+					(f2(c.t60_lf[j][2], c.t60_lf[j + 1][2]) * p[i][0][1]);
+				p[i][0][0] = in;
+				p[i][0][1] = o1;
+				const F2 o2 = (f2(c.t60_hf[j][0], c.t60_hf[j + 1][0]) * o1) + (f2(c.t60_hf[j][1], c.t60_hf[j + 1][1]) * p[i][1][0]) +
+					(f2(c.t60_hf[j][2], c.t60_hf[j + 1][2]) * p[i][1][1]);
+				p[i][1][0] = o1;
+				p[i][1][1] = o2;
+				const F2 out = f2(c.t60_mid[j], c.t60_mid[j + 1]) * o2;
+				sg.at(buf, kWL + j, t) = f2_lo(out);
+				sg.at(buf, kWL + j + 1, t) = f2_hi(out);
+			}
 		}
 	}
 };
@@ -731,8 +853,8 @@ struct EqSingleEcho {
 		}
 		store_words(ef, st_echo);
 	}
-	template <class S>
-	OALSFX_HD void run(const EqualizerCoef& c, const EchoCoef& e, const S& sg, int buf, int count, const LaneMem& ring, int pos0)
+	template <class S, class Sink>
+	OALSFX_HD void run(const EqualizerCoef& c, const EchoCoef& e, const S& sg, int buf, int count, const Sink& out)
 	{
 #if defined(__CUDA_ARCH__)
 #pragma unroll 2
@@ -753,8 +875,8 @@ struct EqSingleEcho {
 				v = y;
 			}
 			sg.at(buf, kWQ + 2, t) = v;
-			const float out = biquad_step(e.filter, ef, sg.at(buf, kWX, t));
-			ring.st((pos0 + t) & e.mask, out * e.feed_gain);
+			const float o = biquad_step(e.filter, ef, sg.at(buf, kWX, t));
+			out.put(kOutEcho, t, o * e.feed_gain);
 		}
 	}
 };
@@ -776,14 +898,12 @@ inline bool emulate_stream(const MixArgs& a, int tile, int lane)
 	const Stage<1, W, CAP> sg = {mem.data()};
 	const int T = a.span_frames, nspans = (a.frames + T - 1) / T;
 	const ReverbCoef& c = a.slot[Cx::RP].u.reverb;
-	ShelfPair shelf[2];
-	T60Pair t60[2];
+	Shelves<2> shelves;
+	T60s<2> t60s;
 	EqPair eqp;
 	EqSingleEcho eqs;
-	for (int p = 0; p < 2; ++p) {
-		shelf[p].load(cx.st_rev, p);
-		t60[p].load(cx.st_rev, p);
-	}
+	shelves.load(cx.st_rev, 0);
+	t60s.load(cx.st_rev, 0);
 	if (CHAIN) {
 		eqp.load(cx.st_eq);
 		eqs.load(cx.st_eq, cx.st_echo);
@@ -800,12 +920,11 @@ inline bool emulate_stream(const MixArgs& a, int tile, int lane)
 	};
 	auto run_b = [&](int s) {
 		const int buf = s % kBuffers, count = count_of(s);
-		for (int p = 1; p >= 0; --p) {
-			t60[p].run(c, sg, buf, count, p);
-			shelf[p].run(c, sg, buf, count, cx.ring_rev, cx.rev_off + s * T, p);
-		}
+		const RingSinkB out = {c, cx.ring_rev, cx.ring_echo, CHAIN ? a.slot[2].u.echo.mask : 0, cx.rev_off + s * T, cx.echo_off + s * T};
+		t60s.run(c, sg, buf, count, 0);
+		shelves.run(c, sg, buf, count, out, 0);
 		if (CHAIN) {
-			eqs.run(a.slot[0].u.equalizer, a.slot[2].u.echo, sg, buf, count, cx.ring_echo, cx.echo_off + s * T);
+			eqs.run(a.slot[0].u.equalizer, a.slot[2].u.echo, sg, buf, count, out);
 			eqp.run(a.slot[0].u.equalizer, sg, buf, count);
 		}
 	};
@@ -813,9 +932,11 @@ inline bool emulate_stream(const MixArgs& a, int tile, int lane)
 		for (int t = count_of(s) - 1; t >= 0; --t) {
 			float x[CT];
 			typename Cx::TapsC k;
+			typename Cx::TapsMod md;
 			cx.load_input(a, s * T + t, x);
-			cx.load_c(a, s * T + t, k);
-			cx.phase_c(a, sg, s % kBuffers, t, s * T + t, x, k);
+			cx.load_c(a, s * T + t, k, md);
+			const RingSinkC out = {c, cx.ring_rev, cx.rev_off + s * T + t};
+			cx.phase_c(a, sg, s % kBuffers, t, s * T + t, x, k, md, out);
 		}
 	};
 	for (int it = -1; it <= nspans; ++it) {
@@ -830,10 +951,230 @@ inline bool emulate_stream(const MixArgs& a, int tile, int lane)
 			}
 		}
 	}
-	for (int p = 0; p < 2; ++p) {
-		shelf[p].store(cx.st_rev, p);
-		t60[p].store(cx.st_rev, p);
+	shelves.store(cx.st_rev, 0);
+	t60s.store(cx.st_rev, 0);
+	if (CHAIN) {
+		eqp.store(cx.st_eq);
+		eqs.store(cx.st_eq, cx.st_echo);
 	}
+	cx.store_scalars(a);
+	cx.store_send_history(a, 0);
+	for (int p = 0; p < (CHAIN ? 4 : 1); ++p) {
+		cx.store_send_history(a, 1 + a.aux_index[p]);
+	}
+	return true;
+}
+
+// ---- span_bulk_kernel: which ring rows its bulk copies move -----------------------------------------------------------------
+// A row = one ring line over the frames of a span: `behind` frames behind the span's ring position, on the reverb's
+// ring region (ring 0) or the echo's (ring 1), line starting at word `word0`, positions modulo mask + 1.
+struct RowJob { int ring, word0, mask, behind; };
+OALSFX_CX int tap_rows_c(bool chain) { return chain ? 18 : 16; }
+OALSFX_CX int tap_rows_a(bool chain) { return chain ? 9 : 8; }
+OALSFX_CX int out_rows_b(bool chain) { return chain ? kOutRowsB : 4; }
+
+template <bool CHAIN>
+OALSFX_HD RowJob reverb_row(const MixArgs& a, int r, int l, int behind)
+{
+	const ReverbCoef& c = a.slot[CHAIN ? 3 : 0].u.reverb;
+	return RowJob{0, c.ring_base[r] + l * (c.mask[r] + 1), c.mask[r], behind};
+}
+// taps of phase C: early 0..3, early all-pass 4..7, early line 8..11, late all-pass 12..15, echo tap1 16, tap2 17
+template <bool CHAIN>
+OALSFX_HD RowJob tap_row_c(const MixArgs& a, int row)
+{
+	const ReverbCoef& c = a.slot[CHAIN ? 3 : 0].u.reverb;
+	const int l = row & 3;
+	switch (row >> 2) {
+	case 0: return reverb_row<CHAIN>(a, 0, l, c.early_tap[l]);
+	case 1: return reverb_row<CHAIN>(a, 1, l, c.early_ap_off[l]);
+	case 2: return reverb_row<CHAIN>(a, 2, l, c.early_off[l]);
+	case 3: return reverb_row<CHAIN>(a, 3, l, c.late_ap_off[l]);
+	default: return RowJob{1, 0, a.slot[2].u.echo.mask, l == 0 ? a.slot[2].u.echo.tap1 : a.slot[2].u.echo.tap2};
+	}
+}
+// taps of phase A: late 0..3, late line 4..7, echo tap2 8
+template <bool CHAIN>
+OALSFX_HD RowJob tap_row_a(const MixArgs& a, int row)
+{
+	const ReverbCoef& c = a.slot[CHAIN ? 3 : 0].u.reverb;
+	const int l = row & 3;
+	switch (row >> 2) {
+	case 0: return reverb_row<CHAIN>(a, 0, l, c.late_tap[l]);
+	case 1: return reverb_row<CHAIN>(a, 4, l, c.late_off[l]);
+	default: return RowJob{1, 0, a.slot[2].u.echo.mask, a.slot[2].u.echo.tap2};
+	}
+}
+// stores of phase C (kOut* rows) and of phase B (main line 0..3, echo 4)
+template <bool CHAIN>
+OALSFX_HD RowJob out_row_c(const MixArgs& a, int row)
+{
+	const ReverbCoef& c = a.slot[CHAIN ? 3 : 0].u.reverb;
+	const int l = row & 3;
+	switch (row >> 2) {
+	case 0: return reverb_row<CHAIN>(a, 1, l, 0);
+	case 1: return reverb_row<CHAIN>(a, 2, l, 0);
+	case 2: return reverb_row<CHAIN>(a, 0, l, c.late_feed_tap);
+	case 3: return reverb_row<CHAIN>(a, 3, l, 0);
+	default: return reverb_row<CHAIN>(a, 4, l, 0);
+	}
+}
+template <bool CHAIN>
+OALSFX_HD RowJob out_row_b(const MixArgs& a, int row)
+{
+	if (row < kOutEcho) {
+		return reverb_row<CHAIN>(a, 0, row, 0);
+	}
+	return RowJob{1, 0, a.slot[2].u.echo.mask, 0};
+}
+
+// One stream through span_bulk_kernel's schedule, executed serially (CPU test build).  The bulk copies are modelled at
+// the extremes of when they may take effect: `late_stores` -- loads at their issue point, stores at the END of the
+// iteration they are issued in (worst case for read-after-write); otherwise stores at their issue point and loads at
+// the end of the iteration they are issued in (worst case for write-after-read).
+template <int CT, bool CHAIN>
+inline bool emulate_stream_bulk(const MixArgs& a, int tile, int lane, bool late_stores)
+{
+	using Cx = Context<CT, CHAIN>;
+	constexpr int W = staged_words(CHAIN), T = kBulkFrames, RC = tap_rows_c(CHAIN), RA = tap_rows_a(CHAIN), RB = out_rows_b(CHAIN);
+	Cx cx;
+	if (!cx.setup(a, tile, lane)) {
+		return false;
+	}
+	std::vector<float> mem(static_cast<size_t>(kBuffers) * W * T), tap_c(2 * RC * T), tap_a(RA * T), out_c(kOutRowsC * T), out_b(2 * RB * T);
+	const Stage<1, W, T> sg = {mem.data()};
+	const int nspans = (a.frames + T - 1) / T;
+	const ReverbCoef& c = a.slot[Cx::RP].u.reverb;
+	Shelves<2> shelves;
+	T60s<2> t60s;
+	EqPair eqp;
+	EqSingleEcho eqs;
+	shelves.load(cx.st_rev, 0);
+	t60s.load(cx.st_rev, 0);
+	if (CHAIN) {
+		eqp.load(cx.st_eq);
+		eqs.load(cx.st_eq, cx.st_echo);
+	}
+	auto count_of = [&](int s) { return a.frames - s * T < T ? a.frames - s * T : T; };
+	std::vector<typename Cx::TapsMod> mod_taps(2 * T);   // the chorus taps are requested together with phase C's rows
+	auto move_row = [&](const RowJob& j, int s, float* row, bool load) {
+		const LaneMem& ring = j.ring == 0 ? cx.ring_rev : cx.ring_echo;
+		const int pos0 = (j.ring == 0 ? cx.rev_off : cx.echo_off) + s * T - j.behind;
+		for (int t = 0; t < count_of(s); ++t) {
+			if (load) {
+				row[t] = ring.ld(j.word0 + ((pos0 + t) & j.mask));
+			} else {
+				ring.st(j.word0 + ((pos0 + t) & j.mask), row[t]);
+			}
+		}
+	};
+	auto load_tap_c = [&](int s) {
+		if (s >= 0 && s < nspans) {
+			for (int r = 0; r < RC; ++r) {
+				move_row(tap_row_c<CHAIN>(a, r), s, &tap_c[((s & 1) * RC + r) * T], true);
+			}
+			if (CHAIN) {
+				for (int t = 0; t < count_of(s); ++t) {
+					cx.load_mod(a, s * T + t, mod_taps[(s & 1) * T + t]);
+				}
+			}
+		}
+	};
+	auto load_tap_a = [&](int s) {
+		if (s >= 0 && s < nspans) {
+			for (int r = 0; r < RA; ++r) {
+				move_row(tap_row_a<CHAIN>(a, r), s, &tap_a[r * T], true);
+			}
+		}
+	};
+	// What iteration `it` issues: phase C's rows of span it - 2, phase B's of span it - 1.  The copies read shared memory
+	// when they are issued (the kernel waits for that before the buffers are written again) and land in the rings later.
+	std::vector<float> pend_c(kOutRowsC * T), pend_b(RB * T);
+	auto issue_stores = [&](int it) {
+		pend_c.assign(out_c.begin(), out_c.end());
+		if (it - 1 >= 0) {
+			pend_b.assign(out_b.begin() + ((it - 1) & 1) * RB * T, out_b.begin() + (((it - 1) & 1) + 1) * RB * T);
+		}
+	};
+	auto land_stores = [&](int it) {
+		if (it - 2 >= 0 && it - 2 < nspans) {
+			for (int r = 0; r < kOutRowsC; ++r) {
+				move_row(out_row_c<CHAIN>(a, r), it - 2, &pend_c[r * T], false);
+			}
+		}
+		if (it - 1 >= 0 && it - 1 < nspans) {
+			for (int r = 0; r < RB; ++r) {
+				move_row(out_row_b<CHAIN>(a, r), it - 1, &pend_b[r * T], false);
+			}
+		}
+	};
+	auto run_a = [&](int s) {
+		for (int t = count_of(s) - 1; t >= 0; --t) {
+			float x[CT];
+			typename Cx::TapsA k;
+			cx.load_input(a, s * T + t, x);
+			cx.template fetch_a<T, 1>(&tap_a[t], k);
+			cx.phase_a(a, sg, s % kBuffers, t, x, k);
+		}
+	};
+	auto run_b = [&](int s) {
+		const int buf = s % kBuffers, count = count_of(s);
+		struct Sink1 { float* base; void put(int row, int t, float v) const { base[row * T + t] = v; } } out1 = {&out_b[(s & 1) * RB * T]};
+		t60s.run(c, sg, buf, count, 0);
+		shelves.run(c, sg, buf, count, out1, 0);
+		if (CHAIN) {
+			eqs.run(a.slot[0].u.equalizer, a.slot[2].u.echo, sg, buf, count, out1);
+			eqp.run(a.slot[0].u.equalizer, sg, buf, count);
+		}
+	};
+	auto run_c = [&](int s) {
+		for (int t = count_of(s) - 1; t >= 0; --t) {
+			float x[CT];
+			typename Cx::TapsC k;
+			cx.load_input(a, s * T + t, x);
+			cx.template fetch_c<T, 1>(&tap_c[(s & 1) * RC * T + t], k);
+			struct Sink1 { float* base; void put(int row, float v) const { base[row * T] = v; } } out1 = {&out_c[t]};
+			cx.phase_c(a, sg, s % kBuffers, t, s * T + t, x, k, mod_taps[(s & 1) * T + t], out1);
+		}
+	};
+	load_tap_a(0);
+	for (int it = -1; it <= nspans + 1; ++it) {
+		issue_stores(it);
+		if (!late_stores) {
+			land_stores(it);
+		} else {
+			load_tap_c(it);
+		}
+		if (it + 1 < nspans) {
+			run_a(it + 1);
+		}
+		if (late_stores) {
+			load_tap_a(it + 2);  // issued once phase A has consumed the buffer
+		}
+		if ((it & 1) != 0) {
+			if (it >= 0 && it < nspans) {
+				run_b(it);
+			}
+			if (it >= 1 && it - 1 < nspans) {
+				run_c(it - 1);
+			}
+		} else {
+			if (it >= 1 && it - 1 < nspans) {
+				run_c(it - 1);
+			}
+			if (it >= 0 && it < nspans) {
+				run_b(it);
+			}
+		}
+		if (late_stores) {
+			land_stores(it);
+		} else {
+			load_tap_a(it + 2);
+			load_tap_c(it);
+		}
+	}
+	shelves.store(cx.st_rev, 0);
+	t60s.store(cx.st_rev, 0);
 	if (CHAIN) {
 		eqp.store(cx.st_eq);
 		eqs.store(cx.st_eq, cx.st_echo);
@@ -953,15 +1294,16 @@ __global__ void __launch_bounds__(threads(CHAIN), 1) span_kernel(const __grid_co
 					const bool two = t2 < count;
 					float x0[CT], x1[CT];
 					typename Cx::TapsC k0, k1;
+					typename Cx::TapsMod m0, m1;
 					cx.load_input(a, first + t, x0);
-					cx.load_c(a, first + t, k0);
+					cx.load_c(a, first + t, k0, m0);
 					if (two) {
 						cx.load_input(a, first + t2, x1);
-						cx.load_c(a, first + t2, k1);
+						cx.load_c(a, first + t2, k1, m1);
 					}
-					cx.phase_c(a, sg, buf, t, first + t, x0, k0);
+					cx.phase_c(a, sg, buf, t, first + t, x0, k0, m0, RingSinkC{c, cx.ring_rev, cx.rev_off + first + t});
 					if (two) {
-						cx.phase_c(a, sg, buf, t2, first + t2, x1, k1);
+						cx.phase_c(a, sg, buf, t2, first + t2, x1, k1, m1, RingSinkC{c, cx.ring_rev, cx.rev_off + first + t2});
 					}
 				}
 			}
@@ -998,33 +1340,39 @@ __global__ void __launch_bounds__(threads(CHAIN), 1) span_kernel(const __grid_co
 		return;
 	}
 
-	// ---- serial warps: B(it), one recurrence each ----
-	const bool active = f == 0;
-	if (w < 2) {
-		ShelfPair r;
-		r.load(cx.st_rev, w);
+	// ---- serial warps: B(it) ----
+	// the reverb's recurrences: both line pairs per thread, or -- a tile shared among CTAs -- one pair per lane group
+	constexpr int NPAIR = SL == kLanes ? 2 : 1;
+	const bool active = f == 0, pair_active = f < 2 / NPAIR;
+	const int p0 = NPAIR == 2 ? 0 : f;
+	auto sink = [&](int it) {
+		return RingSinkB{c, cx.ring_rev, cx.ring_echo, CHAIN ? a.slot[2].u.echo.mask : 0, cx.rev_off + it * T, cx.echo_off + it * T};
+	};
+	if (w == 0) {
+		Shelves<NPAIR> r;
+		r.load(cx.st_rev, pair_active ? p0 : 0);
 		for (int it = -1; it <= nspans; ++it) {
-			if (active && it >= 0 && it < nspans) {
-				r.run(c, sg, it % kBuffers, min(T, a.frames - it * T), cx.ring_rev, cx.rev_off + it * T, w);
+			if (pair_active && it >= 0 && it < nspans) {
+				r.run(c, sg, it % kBuffers, min(T, a.frames - it * T), sink(it), p0);
 			}
 			bar_all();
 		}
-		if (active) {
-			r.store(cx.st_rev, w);
+		if (pair_active) {
+			r.store(cx.st_rev, p0);
 		}
-	} else if (w < 4) {
-		T60Pair r;
-		r.load(cx.st_rev, w - 2);
+	} else if (w == 1) {
+		T60s<NPAIR> r;
+		r.load(cx.st_rev, pair_active ? p0 : 0);
 		for (int it = -1; it <= nspans; ++it) {
-			if (active && it >= 0 && it < nspans) {
-				r.run(c, sg, it % kBuffers, min(T, a.frames - it * T), w - 2);
+			if (pair_active && it >= 0 && it < nspans) {
+				r.run(c, sg, it % kBuffers, min(T, a.frames - it * T), p0);
 			}
 			bar_all();
 		}
-		if (active) {
-			r.store(cx.st_rev, w - 2);
+		if (pair_active) {
+			r.store(cx.st_rev, p0);
 		}
-	} else if (CHAIN && w == 4) {
+	} else if (CHAIN && w == 2) {
 		EqPair r;
 		r.load(cx.st_eq);
 		for (int it = -1; it <= nspans; ++it) {
@@ -1041,13 +1389,311 @@ __global__ void __launch_bounds__(threads(CHAIN), 1) span_kernel(const __grid_co
 		r.load(cx.st_eq, cx.st_echo);
 		for (int it = -1; it <= nspans; ++it) {
 			if (active && it >= 0 && it < nspans) {
-				r.run(a.slot[0].u.equalizer, a.slot[2].u.echo, sg, it % kBuffers, min(T, a.frames - it * T), cx.ring_echo, cx.echo_off + it * T);
+				r.run(a.slot[0].u.equalizer, a.slot[2].u.echo, sg, it % kBuffers, min(T, a.frames - it * T), sink(it));
 			}
 			bar_all();
 		}
 		if (active) {
 			r.store(cx.st_eq, cx.st_echo);
 		}
+	}
+}
+
+// ---- the same pipeline with bulk-asynchronous ring traffic (whole tiles) ---------------------------------------------
+// A span's T = 16 positions of one ring line are ONE contiguous run of 16 x 128 bytes (the rings are line-major), so
+// the ring traffic of a span is a handful of bulk copies (cp.async.bulk, the 1-D TMA path) instead of ~60 address
+// computations + 4-byte requests per frame: 18 + 9 row loads global -> shared (mbarrier complete_tx) and 20 + 5 row
+// stores shared -> global (bulk groups) per span, issued by the lanes of one warp; the phases then read and write
+// shared-memory rows at immediate offsets.  Loads are issued ahead and stores behind the arithmetic (Timing kBulkTiming,
+// checked per coefficient block by plan_bulk_frames).  Only the chorus / flanger -- LFO-modulated positions, two reads and
+// two writes per frame -- stays on ordinary loads and stores.
+//
+// Shared memory (rows of 16 x 32 floats = 2 KB): tapC[2][18] | tapA[9] | outC[20] | outB[2][5] | staged words [3][12]
+// = 222 KB for the chain.  Per iteration `it` (B of span it):
+//   DMA lanes (serial warp 1): store outC(it-2), outB(it-1) -> rings; load tapC(it); wait until the stores have read
+//                              shared memory; arrive at barrier P; ... (own phase B) ...; wait for the stores to land
+//   parallel warps:            A(it+1) from tapA; barrier P; [warp 0: load tapA(it+2)]; C(it-1) from tapC, into outC
+//   serial warps:              B(it), main line / echo ring rows into outB
+//   everybody:                 fence.proxy.async, CTA barrier
+OALSFX_CX int bulk_shared_floats(bool chain)
+{
+	return (2 * tap_rows_c(chain) + tap_rows_a(chain) + kOutRowsC + 2 * out_rows_b(chain) + kBuffers * staged_words(chain)) * kBulkFrames * kLanes;
+}
+
+__device__ __forceinline__ unsigned shared_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(shared_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(shared_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+{
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"WAIT_%=:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra DONE_%=;\n"
+		"bra WAIT_%=;\n"
+		"DONE_%=:\n"
+		"}\n" ::"r"(shared_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(float* smem_dst, const float* gmem_src, unsigned bytes, uint64_t* bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		::"r"(shared_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(shared_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_store(float* gmem_dst, const float* smem_src, unsigned bytes)
+{
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(shared_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// `count` rows of a ring line starting at position pos0 (modulo mask + 1) <-> a shared-memory row buffer
+__device__ __forceinline__ void move_rows(bool load, float* line, int mask, int pos0, int count, float* smem_row, uint64_t* bar)
+{
+	const int start = pos0 & mask;
+	const int n1 = min(count, mask + 1 - start);
+	if (load) {
+		bulk_load(smem_row, line + static_cast<size_t>(start) * kLanes, static_cast<unsigned>(n1) * kLanes * 4U, bar);
+		if (n1 < count) {
+			bulk_load(smem_row + n1 * kLanes, line, static_cast<unsigned>(count - n1) * kLanes * 4U, bar);
+		}
+	} else {
+		bulk_store(line + static_cast<size_t>(start) * kLanes, smem_row, static_cast<unsigned>(n1) * kLanes * 4U);
+		if (n1 < count) {
+			bulk_store(line, smem_row + n1 * kLanes, static_cast<unsigned>(count - n1) * kLanes * 4U);
+		}
+	}
+}
+
+template <int CT, bool CHAIN>
+__global__ void __launch_bounds__(threads(CHAIN), 1) span_bulk_kernel(const __grid_constant__ MixArgs a)
+{
+	using Cx = Context<CT, CHAIN>;
+	constexpr int NS = serial_warps(CHAIN), NP = kParallelWarps, T = kBulkFrames, W = staged_words(CHAIN);
+	constexpr int RC = tap_rows_c(CHAIN), RA = tap_rows_a(CHAIN), RB = out_rows_b(CHAIN), ROW = T * kLanes;
+	constexpr int kDmaWarp = 1;                       // the T60 warp also issues the copies
+	constexpr unsigned kBarP = 1, kBarPThreads = (NP + 1) * kLanes;
+	extern __shared__ __align__(128) float dyn[];
+	float* const tap_c = dyn;                         // [2][RC][T][lane]
+	float* const tap_a = tap_c + 2 * RC * ROW;        // [RA][T][lane]
+	float* const out_c = tap_a + RA * ROW;            // [kOutRowsC][T][lane]
+	float* const out_b = out_c + kOutRowsC * ROW;     // [2][RB][T][lane]
+	float* const staged = out_b + 2 * RB * ROW;       // [3][W][T][lane]
+	__shared__ __align__(8) uint64_t mbar[3];         // tapC[0], tapC[1], tapA
+
+	const int tile = a.tiles ? static_cast<int>(a.tiles[blockIdx.x].tile) : a.tile_first + static_cast<int>(blockIdx.x);
+	const int lane = threadIdx.x % kLanes;
+	const int w = threadIdx.x / kLanes;
+
+	Cx cx;
+	bool ok = cx.setup(a, tile, lane);
+	// the copies move whole rows: every stream of the tile must sit at the same ring positions
+	ok = ok && cx.rev_off == __shfl_sync(0xFFFFFFFFU, cx.rev_off, 0);
+	if (CHAIN) {
+		ok = ok && cx.echo_off == __shfl_sync(0xFFFFFFFFU, cx.echo_off, 0);
+	}
+	ok = ok || !cx.io_ok;  // lanes past the last stream: their rings exist, their results are never looked at
+	if (threadIdx.x == 0) {
+		mbar_init(&mbar[0], 1);
+		mbar_init(&mbar[1], 1);
+		mbar_init(&mbar[2], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	if (!__syncthreads_and(ok)) {
+		if (w == 0 && cx.io_ok) {
+			exact_stream<CT, CHAIN>(a, tile, lane);
+		}
+		return;
+	}
+	const Stage<kLanes, W, T> sg = {staged + lane};
+	const int nspans = (a.frames + T - 1) / T;
+	const ReverbCoef& c = a.slot[Cx::RP].u.reverb;
+	float* const tile_rev = cx.ring_rev.p - lane;
+	float* const tile_echo = CHAIN ? cx.ring_echo.p - lane : nullptr;
+	auto count_of = [&](int s) { return min(T, a.frames - s * T); };
+	// one row job per lane
+	auto move = [&](bool load, const RowJob& j, int s, float* smem_row, uint64_t* bar) {
+		move_rows(load, (j.ring == 0 ? tile_rev : tile_echo) + static_cast<size_t>(j.word0) * kLanes, j.mask,
+			(j.ring == 0 ? cx.rev_off : cx.echo_off) + s * T - j.behind, count_of(s), smem_row, bar);
+	};
+	auto load_tap_a = [&](int s) {                   // whole warp; lanes 0 .. RA-1 move a row each
+		if (s < nspans) {
+			if (lane == 0) {
+				mbar_expect_tx(&mbar[2], static_cast<unsigned>(RA * count_of(s) * kLanes * 4));
+			}
+			__syncwarp();
+			if (lane < RA) {
+				move(true, tap_row_a<CHAIN>(a, lane), s, tap_a + lane * ROW, &mbar[2]);
+			}
+		}
+	};
+
+	if (w >= NS) {
+		// ---- parallel warps ----
+		const int pw = w - NS;
+		constexpr int U = T / NP;                    // frames of a span per warp: t = pw + u * NP
+		if (pw == 0) {
+			load_tap_a(0);
+		}
+		// Everything a frame needs besides the ring rows -- its input and (chain) its two chorus taps, LFO-modulated
+		// positions that stay on ordinary loads -- is requested one iteration ahead and parked in registers.
+		float xa[U][CT], xc[U][CT];
+		typename Cx::TapsMod md[U];
+#pragma unroll
+		for (int u = 0; u < U; ++u) {
+			cx.load_input(a, min(pw + u * NP, a.frames - 1), xa[u]);   // phase A of span 0
+#pragma unroll
+			for (int ch = 0; ch < CT; ++ch) {
+				xc[u][ch] = 0.0F;
+			}
+			md[u].v[0] = md[u].v[1] = 0.0F;
+			md[u].pos = 0;
+		}
+		for (int it = -1; it <= nspans; ++it) {
+			float xa_next[U][CT], xc_next[U][CT];
+			typename Cx::TapsMod md_next[U];
+#pragma unroll
+			for (int u = 0; u < U; ++u) {
+				const int na = min((it + 2) * T + pw + u * NP, a.frames - 1);   // phase A of span it + 2
+				const int nc = min(max(it, 0) * T + pw + u * NP, a.frames - 1); // phase C of span it
+				cx.load_input(a, na, xa_next[u]);
+				cx.load_input(a, nc, xc_next[u]);
+				if (CHAIN) {
+					cx.load_mod(a, nc, md_next[u]);
+				}
+			}
+			if (it + 1 < nspans) {
+				const int s = it + 1, buf = s % kBuffers, count = count_of(s);
+				mbar_wait(&mbar[2], static_cast<unsigned>(s & 1));
+#pragma unroll
+				for (int u = 0; u < U; ++u) {
+					const int t = pw + u * NP;
+					if (t < count) {
+						typename Cx::TapsA k;
+						cx.template fetch_a<T, kLanes>(tap_a + t * kLanes + lane, k);
+						cx.phase_a(a, sg, buf, t, xa[u], k);
+					}
+				}
+			}
+			asm volatile("bar.sync %0, %1;" ::"n"(kBarP), "n"(kBarPThreads) : "memory");
+			if (pw == 0) {
+				load_tap_a(it + 2);                  // every warp is through with the buffer
+			}
+			if (it >= 1) {
+				const int s = it - 1, buf = s % kBuffers, first = s * T, count = count_of(s);
+				mbar_wait(&mbar[s & 1], static_cast<unsigned>((s >> 1) & 1));
+				const float* rows = tap_c + (s & 1) * RC * ROW + lane;
+#pragma unroll
+				for (int u = 0; u < U; ++u) {
+					const int t = pw + u * NP;
+					if (t < count) {
+						typename Cx::TapsC k;
+						cx.template fetch_c<T, kLanes>(rows + t * kLanes, k);
+						cx.phase_c(a, sg, buf, t, first + t, xc[u], k, md[u], StageSinkC<T>{out_c + t * kLanes + lane});
+					}
+				}
+			}
+#pragma unroll
+			for (int u = 0; u < U; ++u) {
+#pragma unroll
+				for (int ch = 0; ch < CT; ++ch) {
+					xa[u][ch] = xa_next[u][ch];
+					xc[u][ch] = xc_next[u][ch];
+				}
+				md[u] = md_next[u];
+			}
+			fence_async_shared();
+			bar_all();
+		}
+		if (pw == 0) {
+			cx.store_scalars(a);
+		} else if (pw == 1) {
+			cx.store_send_history(a, 0);
+		} else if (pw - 2 < (CHAIN ? 4 : 1)) {
+			cx.store_send_history(a, 1 + a.aux_index[pw - 2]);
+		}
+		return;
+	}
+
+	// ---- serial warps ----
+	const StageSinkB<T> sink0 = {out_b + lane}, sink1 = {out_b + RB * ROW + lane};
+	if (w == kDmaWarp) {
+		T60s<2> r;
+		r.load(cx.st_rev, 0);
+		for (int it = -1; it <= nspans + 1; ++it) {
+			// rows written in the previous iteration -> rings
+			if (it - 2 >= 0 && it - 2 < nspans && lane < kOutRowsC) {
+				move(false, out_row_c<CHAIN>(a, lane), it - 2, out_c + lane * ROW, nullptr);
+			}
+			if (it - 1 >= 0 && it - 1 < nspans && lane >= kOutRowsC && lane < kOutRowsC + RB) {
+				move(false, out_row_b<CHAIN>(a, lane - kOutRowsC), it - 1, out_b + (((it - 1) & 1) * RB + lane - kOutRowsC) * ROW, nullptr);
+			}
+			bulk_commit();
+			if (it > nspans) {
+				bulk_wait_all();
+				break;
+			}
+			// phase C's rows of span `it`, consumed in the next iteration
+			if (it >= 0 && it < nspans) {
+				if (lane == 0) {
+					mbar_expect_tx(&mbar[it & 1], static_cast<unsigned>(RC * count_of(it) * kLanes * 4));
+				}
+				__syncwarp();
+				if (lane < RC) {
+					move(true, tap_row_c<CHAIN>(a, lane), it, tap_c + ((it & 1) * RC + lane) * ROW, &mbar[it & 1]);
+				}
+			}
+			bulk_wait_read();                        // outC / outB may be written again
+			asm volatile("bar.arrive %0, %1;" ::"n"(kBarP), "n"(kBarPThreads) : "memory");
+			if (it >= 0 && it < nspans) {
+				r.run(c, sg, it % kBuffers, count_of(it), 0);
+			}
+			bulk_wait_all();                         // this iteration's stores have landed
+			fence_async_shared();
+			bar_all();
+		}
+		r.store(cx.st_rev, 0);
+	} else if (w == 0) {
+		Shelves<2> r;
+		r.load(cx.st_rev, 0);
+		for (int it = -1; it <= nspans; ++it) {
+			if (it >= 0 && it < nspans) {
+				r.run(c, sg, it % kBuffers, count_of(it), (it & 1) ? sink1 : sink0, 0);
+			}
+			fence_async_shared();
+			bar_all();
+		}
+		r.store(cx.st_rev, 0);
+	} else if (CHAIN && w == 2) {
+		EqPair r;
+		r.load(cx.st_eq);
+		for (int it = -1; it <= nspans; ++it) {
+			if (it >= 0 && it < nspans) {
+				r.run(a.slot[0].u.equalizer, sg, it % kBuffers, count_of(it));
+			}
+			fence_async_shared();
+			bar_all();
+		}
+		r.store(cx.st_eq);
+	} else if (CHAIN) {
+		EqSingleEcho r;
+		r.load(cx.st_eq, cx.st_echo);
+		for (int it = -1; it <= nspans; ++it) {
+			if (it >= 0 && it < nspans) {
+				r.run(a.slot[0].u.equalizer, a.slot[2].u.echo, sg, it % kBuffers, count_of(it), (it & 1) ? sink1 : sink0);
+			}
+			fence_async_shared();
+			bar_all();
+		}
+		r.store(cx.st_eq, cx.st_echo);
 	}
 }
 

@@ -19,6 +19,7 @@ namespace oalsfx {
 namespace {
 
 long long g_span_streams = 0; // streams x launches that took the span schedule (read by the tests)
+long long g_span_bulk_streams = 0; // ... of those, with the bulk-copy timing
 
 class HostBackend final : public Backend {
 public:
@@ -121,15 +122,35 @@ public:
 #define OALSFX_SX(id, CT, SL, CHAIN) if (kernel_id == id) { span_twin = (CHAIN ? kChainStereo : CT == 1 ? kReverbMono : kReverbStereo); }
 		OALSFX_SPAN_TABLE(OALSFX_SX)
 #undef OALSFX_SX
+		bool bulk = false;
+#define OALSFX_BX(id, CT, CHAIN) if (kernel_id == id) { span_twin = (CHAIN ? kChainStereo : CT == 1 ? kReverbMono : kReverbStereo); bulk = true; }
+		OALSFX_SPAN_BULK_TABLE(OALSFX_BX)
+#undef OALSFX_BX
 		if (span_twin >= 0) {
+			static int launch_parity = 0;
+			const bool late_stores = bulk && (++launch_parity & 1);
 			for (int w = 0; w < a.tile_count; ++w) {
 				const int tile = a.tiles ? static_cast<int>(a.tiles[w].tile) : a.tile_first + w;
 				// the device decides per CTA (= per tile, or per share of a tile); per tile here
 				bool steady = true;
+				int32_t off0[2] = {0, 0};
 				for (int lane = 0; lane < kLanes && steady; ++lane) {
 					if (tile * kLanes + lane < a.num_streams) {
-						steady = span_twin == kChainStereo ? span::Context<2, true>().setup(a, tile, lane) :
-							span_twin == kReverbMono ? span::Context<1, false>().setup(a, tile, lane) : span::Context<2, false>().setup(a, tile, lane);
+						int32_t off[2] = {0, 0};
+						auto probe = [&](auto cx) {
+							const bool ok = cx.setup(a, tile, lane);
+							off[0] = cx.rev_off;
+							off[1] = span_twin == kChainStereo ? cx.echo_off : 0;
+							return ok;
+						};
+						steady = span_twin == kChainStereo ? probe(span::Context<2, true>()) :
+							span_twin == kReverbMono ? probe(span::Context<1, false>()) : probe(span::Context<2, false>());
+						if (lane == 0) {
+							off0[0] = off[0];
+							off0[1] = off[1];
+						}
+						// the bulk kernel moves whole rows: every stream of the tile at the same ring positions
+						steady = steady && (!bulk || (off[0] == off0[0] && off[1] == off0[1]));
 					}
 				}
 				for (int lane = 0; lane < kLanes; ++lane) {
@@ -144,6 +165,15 @@ public:
 						}
 					} else {
 						++g_span_streams;
+						if (bulk) {
+							++g_span_bulk_streams;
+							switch (span_twin) {
+							case kChainStereo: span::emulate_stream_bulk<2, true>(a, tile, lane, late_stores); break;
+							case kReverbMono: span::emulate_stream_bulk<1, false>(a, tile, lane, late_stores); break;
+							default: span::emulate_stream_bulk<2, false>(a, tile, lane, late_stores); break;
+							}
+							continue;
+						}
 						switch (span_twin) {
 						case kChainStereo: span::emulate_stream<2, true>(a, tile, lane); break;
 						case kReverbMono: span::emulate_stream<1, false>(a, tile, lane); break;
@@ -244,6 +274,7 @@ private:
 
 Backend* make_backend(int, std::string&) { return new HostBackend; }
 extern "C" long long oalsfx_emu_span_streams() { return g_span_streams; }
+extern "C" long long oalsfx_emu_span_bulk_streams() { return g_span_bulk_streams; }
 const char* backend_build_info() { return "oalsfx host-emu (tests only)"; }
 
 } // namespace oalsfx

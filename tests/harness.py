@@ -102,6 +102,7 @@ def emu_lib():
         build_emu()
         _CACHE["emu"] = _eng.bind(C.CDLL(os.path.join(ROOT, "tests", "_build", "liboalsfx_emu.so")))
         _CACHE["emu"].oalsfx_emu_span_streams.restype = C.c_longlong
+        _CACHE["emu"].oalsfx_emu_span_bulk_streams.restype = C.c_longlong
     return _CACHE["emu"]
 
 

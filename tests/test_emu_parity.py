@@ -192,6 +192,15 @@ def test_span_chain_schedule_and_legality(checker, case, monkeypatch):
     assert H.emu_lib().oalsfx_emu_span_streams() > before
 
 
+@pytest.mark.parametrize("case", ["default", "flanger-96k", "forest-short-echo", "short-first-blocks", "standard-reverb", "eax-mono"])
+def test_span_bulk_schedule_and_legality(checker, case, monkeypatch):
+    """span_bulk_kernel's timing (row loads issued one / two iterations ahead, row stores landing one / two behind),
+    emulated at both extremes of when the copies may take effect."""
+    before = H.emu_lib().oalsfx_emu_span_bulk_streams()
+    _gpu_scenarios(monkeypatch).test_span_bulk_kernel(checker, case, monkeypatch)
+    assert H.emu_lib().oalsfx_emu_span_bulk_streams() > before
+
+
 def test_span_schedule_was_taken_for_the_single_reverb_slot(checker, monkeypatch):
     before = H.emu_lib().oalsfx_emu_span_streams()
     _gpu_scenarios(monkeypatch).test_span_kernel_on_steady_state_blocks(checker, "eax-stereo")

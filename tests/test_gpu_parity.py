@@ -336,6 +336,17 @@ def test_span_kernel_on_steady_state_blocks(checker, case):
         _assert_match(expect, y[s], True, f"span {case} stream {s}")
 
 
+@pytest.mark.parametrize("case", ["default", "flanger-96k", "forest-short-echo", "short-first-blocks", "standard-reverb", "eax-mono"])
+def test_span_bulk_kernel(checker, case, monkeypatch):
+    """span_bulk_kernel: the same pipeline with the ring rows of a span moved by bulk copies (issued ahead of / behind the
+    arithmetic, so with its own legality rule).  OALSFX_SPAN_BULK=2 selects it however few tiles the engine has."""
+    monkeypatch.setenv("OALSFX_SPAN_BULK", "2")
+    if case == "eax-mono":
+        test_span_kernel_on_steady_state_blocks(checker, case)
+    else:
+        test_span_chain_on_steady_state_blocks(checker, case)
+
+
 @pytest.mark.parametrize("case", ["default", "flanger-96k", "forest-short-echo", "short-first-blocks", "standard-reverb"])
 def test_span_chain_on_steady_state_blocks(checker, case):
     """span.cuh on the 4-slot chain: blocks without a pending update run equalizer + chorus / flanger + echo + reverb
