@@ -26,7 +26,7 @@ bool launch_span_family(int kernel_id, const MixArgs& args, cudaStream_t st)
 			cudaFuncSetAttribute(span::span_bulk_kernel<CT, CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)); \
 			done[id] = true; \
 		} \
-		span::span_bulk_kernel<CT, CHAIN><<<static_cast<unsigned>(args.tile_count), span::threads(CHAIN), bytes, st>>>(args); \
+		span::span_bulk_kernel<CT, CHAIN><<<static_cast<unsigned>(args.tile_count), span::bulk_threads(CHAIN), bytes, st>>>(args); \
 		return true; }
 		OALSFX_SPAN_BULK_TABLE(OALSFX_BX)
 #undef OALSFX_BX

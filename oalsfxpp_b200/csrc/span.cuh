@@ -73,38 +73,40 @@ constexpr int kPhA = -1, kPhB = 0, kPhC = 1;
 struct Legality {
 	int t;
 	bool ok = true;
-	// A read `delay` frames behind the frame position in phase pr against a write `wofs` frames behind it in
-	// phase pw, on a ring of `len` positions.  zero_is_new: a read of the position written in the same frame
-	// sees the new value (the reference writes first), else the one written `len` frames earlier.
-	void pair(int pr, int delay, int pw, int wofs, int len, bool zero_is_new)
+	// A read `delay` frames behind the frame position in iteration offset pr against a write `wofs` frames behind it
+	// that lands in iteration offsets [pw0, pw1], on a ring of `len` positions.  zero_is_new: a read of the position
+	// written in the same frame sees the new value (the reference writes first), else the one written `len` frames earlier.
+	void pair(int pr, int delay, int pw0, int pw1, int wofs, int len, bool zero_is_new)
 	{
 		int k = ((delay - wofs) % len + len) % len;  // frames between the write of a position and this read of it
 		if (k == 0 && !zero_is_new) {
 			k = len;
 		}
-		// read after write: writer in iteration span(n - k) + pw, reader in span(n) + pr; min over n of the span
-		// difference is floor(k / t)
-		ok = ok && k / t > pw - pr;
-		// write after read: the position is next written len - k frames after the read
-		ok = ok && (len - k) / t > pr - pw;
+		// read after write: the write has landed by iteration span(n - k) + pw1, the read happens in span(n) + pr; the
+		// minimum over n of the span difference is floor(k / t)
+		ok = ok && k / t > pw1 - pr;
+		// write after read: the position is next written len - k frames after the read, not before span(..) + pw0
+		ok = ok && (len - k) / t > pr - pw0;
 	}
 	// two writers of one ring: the writes to a position keep their order
-	void writers(int p1, int o1, int p2, int o2, int len)
+	void writers(int p10, int p11, int o1, int p20, int p21, int o2, int len)
 	{
 		const int d = ((o2 - o1) % len + len) % len;   // writer 2 reaches a position d frames after writer 1
-		ok = ok && d / t > p1 - p2;
-		ok = ok && (len - d) / t > p2 - p1;
+		ok = ok && d / t > p11 - p20;
+		ok = ok && (len - d) / t > p21 - p10;
 	}
 };
 
 // When the ring accesses of a span's phases take effect, as iteration offsets from the span index:
-//   ra / rc  reads of phase A / C,   wb / wc  writes of phase B / C,   mr / mw  the chorus ring's reads / writes
-// span_kernel (loads and stores at the point of use):       A one iteration before B, C one after
+//   ra / rc  reads of phase A / C;  wb / wc  writes of phase B / C: [first, last] iteration they may land in;
+//   mr / mw  the chorus ring's reads / writes
+// span_kernel (loads and stores at the point of use):        A one iteration before B, C one after
 // span_bulk_kernel (bulk copies issued ahead, stores behind): A's rows fetched two iterations before B, C's in B's own
-//   iteration; B's stores land one iteration after B, C's two; the chorus taps are requested one iteration before C
-struct Timing { int ra, rc, wb, wc, mr, mw; };
-constexpr Timing kDirectTiming = {kPhA, kPhC, kPhB, kPhC, kPhC, kPhC};
-constexpr Timing kBulkTiming = {-2, 0, 1, 2, 0, 1};
+//   iteration; B's row stores are issued when B is done and have landed by the end of the next iteration, C's
+//   likewise (C runs one iteration after B); the chorus taps are requested one iteration before C
+struct Timing { int ra, rc, wb0, wb1, wc0, wc1, mr, mw; };
+constexpr Timing kDirectTiming = {kPhA, kPhC, kPhB, kPhB, kPhC, kPhC, kPhC, kPhC};
+constexpr Timing kBulkTiming = {-2, 0, 0, 1, 1, 2, 0, 1};
 constexpr int kBulkFrames = 16;           // span length of span_bulk_kernel (shared memory holds every ring row of a span)
 
 inline bool reverb_legal(const ReverbCoef& c, int t, const Timing& tm = kDirectTiming)
@@ -117,16 +119,16 @@ inline bool reverb_legal(const ReverbCoef& c, int t, const Timing& tm = kDirectT
 	const int len0 = c.mask[0] + 1;
 	for (int l = 0; l < 4; ++l) {
 		// main line: shelves write at the position (B), the early scatter feeds it late_feed_tap behind (C)
-		g.pair(tm.rc, c.early_tap[l], tm.wb, 0, len0, true);
-		g.pair(tm.rc, c.early_tap[l], tm.wc, c.late_feed_tap, len0, false);
-		g.pair(tm.ra, c.late_tap[l], tm.wb, 0, len0, true);
-		g.pair(tm.ra, c.late_tap[l], tm.wc, c.late_feed_tap, len0, true);
-		g.pair(tm.rc, c.early_ap_off[l], tm.wc, 0, c.mask[1] + 1, false);
-		g.pair(tm.rc, c.early_off[l], tm.wc, 0, c.mask[2] + 1, true);
-		g.pair(tm.rc, c.late_ap_off[l], tm.wc, 0, c.mask[3] + 1, false);
-		g.pair(tm.ra, c.late_off[l], tm.wc, 0, c.mask[4] + 1, true);
+		g.pair(tm.rc, c.early_tap[l], tm.wb0, tm.wb1, 0, len0, true);
+		g.pair(tm.rc, c.early_tap[l], tm.wc0, tm.wc1, c.late_feed_tap, len0, false);
+		g.pair(tm.ra, c.late_tap[l], tm.wb0, tm.wb1, 0, len0, true);
+		g.pair(tm.ra, c.late_tap[l], tm.wc0, tm.wc1, c.late_feed_tap, len0, true);
+		g.pair(tm.rc, c.early_ap_off[l], tm.wc0, tm.wc1, 0, c.mask[1] + 1, false);
+		g.pair(tm.rc, c.early_off[l], tm.wc0, tm.wc1, 0, c.mask[2] + 1, true);
+		g.pair(tm.rc, c.late_ap_off[l], tm.wc0, tm.wc1, 0, c.mask[3] + 1, false);
+		g.pair(tm.ra, c.late_off[l], tm.wc0, tm.wc1, 0, c.mask[4] + 1, true);
 	}
-	g.writers(tm.wb, 0, tm.wc, c.late_feed_tap, len0);
+	g.writers(tm.wb0, tm.wb1, 0, tm.wc0, tm.wc1, c.late_feed_tap, len0);
 	return g.ok;
 }
 
@@ -139,8 +141,8 @@ inline bool mod_delay_legal(const ModDelayCoef& c, int t, const Timing& tm = kDi
 	if (dmin < 1 || c.lfo_range <= kMaxBlockFrames) {
 		return false;
 	}
-	g.pair(tm.mr, dmin, tm.mw, 0, c.mask + 1, false);
-	g.pair(tm.mr, dmax, tm.mw, 0, c.mask + 1, false);
+	g.pair(tm.mr, dmin, tm.mw, tm.mw, 0, c.mask + 1, false);
+	g.pair(tm.mr, dmax, tm.mw, tm.mw, 0, c.mask + 1, false);
 	return g.ok && dmax < c.mask + 1;
 }
 
@@ -148,9 +150,9 @@ inline bool echo_legal(const EchoCoef& c, int t, const Timing& tm = kDirectTimin
 {
 	Legality g;
 	g.t = t;
-	g.pair(tm.rc, c.tap1, tm.wb, 0, c.mask + 1, false);
-	g.pair(tm.rc, c.tap2, tm.wb, 0, c.mask + 1, false);
-	g.pair(tm.ra, c.tap2, tm.wb, 0, c.mask + 1, false);
+	g.pair(tm.rc, c.tap1, tm.wb0, tm.wb1, 0, c.mask + 1, false);
+	g.pair(tm.rc, c.tap2, tm.wb0, tm.wb1, 0, c.mask + 1, false);
+	g.pair(tm.ra, c.tap2, tm.wb0, tm.wb1, 0, c.mask + 1, false);
 	return g.ok;
 }
 
@@ -263,6 +265,17 @@ template <int T>
 struct StageSinkC {
 	float* base;                  // + frame * 32 + lane
 	OALSFX_HD void put(int row, float v) const { base[row * (T * kLanes)] = v; }
+};
+// ... where phase C's store rows replace the tap rows the same thread has just read: early all-pass and early line
+// rows in place of their taps, the main-line feed in place of the early taps, late all-pass in place, the late line
+// in place of the echo taps + two spare rows (buffer rows: early 0..3, early all-pass 4..7, early line 8..11, late
+// all-pass 12..15, echo taps 16, 17)
+OALSFX_CX int buffer_row_of_out(int out_row) { return out_row < kOutFeed ? out_row + 4 : out_row < kOutLap ? out_row - kOutFeed : out_row; }
+OALSFX_CX int out_of_buffer_row(int row) { return row < 4 ? kOutFeed + row : row < 12 ? row - 4 : row; }
+template <int T>
+struct InPlaceSinkC {
+	float* base;                  // + frame * 32 + lane
+	OALSFX_HD void put(int row, float v) const { base[buffer_row_of_out(row) * (T * kLanes)] = v; }
 };
 template <int T>
 struct StageSinkB {
@@ -1041,7 +1054,7 @@ inline bool emulate_stream_bulk(const MixArgs& a, int tile, int lane, bool late_
 	if (!cx.setup(a, tile, lane)) {
 		return false;
 	}
-	std::vector<float> mem(static_cast<size_t>(kBuffers) * W * T), tap_c(2 * RC * T), tap_a(RA * T), out_c(kOutRowsC * T), out_b(2 * RB * T);
+	std::vector<float> mem(static_cast<size_t>(kBuffers) * W * T), tap_c(2 * RC * T), tap_a(RA * T), out_c(kOutRowsC * T), out_b(RB * T);
 	const Stage<1, W, T> sg = {mem.data()};
 	const int nspans = (a.frames + T - 1) / T;
 	const ReverbCoef& c = a.slot[Cx::RP].u.reverb;
@@ -1087,27 +1100,24 @@ inline bool emulate_stream_bulk(const MixArgs& a, int tile, int lane, bool late_
 			}
 		}
 	};
-	// What iteration `it` issues: phase C's rows of span it - 2, phase B's of span it - 1.  The copies read shared memory
-	// when they are issued (the kernel waits for that before the buffers are written again) and land in the rings later.
-	std::vector<float> pend_c(kOutRowsC * T), pend_b(RB * T);
-	auto issue_stores = [&](int it) {
-		pend_c.assign(out_c.begin(), out_c.end());
-		if (it - 1 >= 0) {
-			pend_b.assign(out_b.begin() + ((it - 1) & 1) * RB * T, out_b.begin() + (((it - 1) & 1) + 1) * RB * T);
-		}
-	};
-	auto land_stores = [&](int it) {
-		if (it - 2 >= 0 && it - 2 < nspans) {
+	// The row stores are issued by the warp that produced the rows, right after the phase, and may land any time up
+	// to the end of the following iteration.
+	auto land_c = [&](int s, const float* rows) {
+		if (s >= 0 && s < nspans) {
 			for (int r = 0; r < kOutRowsC; ++r) {
-				move_row(out_row_c<CHAIN>(a, r), it - 2, &pend_c[r * T], false);
-			}
-		}
-		if (it - 1 >= 0 && it - 1 < nspans) {
-			for (int r = 0; r < RB; ++r) {
-				move_row(out_row_b<CHAIN>(a, r), it - 1, &pend_b[r * T], false);
+				move_row(out_row_c<CHAIN>(a, r), s, const_cast<float*>(rows) + r * T, false);
 			}
 		}
 	};
+	auto land_b = [&](int s, const float* rows) {
+		if (s >= 0 && s < nspans) {
+			for (int r = 0; r < RB; ++r) {
+				move_row(out_row_b<CHAIN>(a, r), s, const_cast<float*>(rows) + r * T, false);
+			}
+		}
+	};
+	std::vector<float> pend_c[2] = {std::vector<float>(kOutRowsC * T), std::vector<float>(kOutRowsC * T)};
+	std::vector<float> pend_b[2] = {std::vector<float>(RB * T), std::vector<float>(RB * T)};
 	auto run_a = [&](int s) {
 		for (int t = count_of(s) - 1; t >= 0; --t) {
 			float x[CT];
@@ -1119,7 +1129,7 @@ inline bool emulate_stream_bulk(const MixArgs& a, int tile, int lane, bool late_
 	};
 	auto run_b = [&](int s) {
 		const int buf = s % kBuffers, count = count_of(s);
-		struct Sink1 { float* base; void put(int row, int t, float v) const { base[row * T + t] = v; } } out1 = {&out_b[(s & 1) * RB * T]};
+		struct Sink1 { float* base; void put(int row, int t, float v) const { base[row * T + t] = v; } } out1 = {out_b.data()};
 		t60s.run(c, sg, buf, count, 0);
 		shelves.run(c, sg, buf, count, out1, 0);
 		if (CHAIN) {
@@ -1139,11 +1149,8 @@ inline bool emulate_stream_bulk(const MixArgs& a, int tile, int lane, bool late_
 	};
 	load_tap_a(0);
 	for (int it = -1; it <= nspans + 1; ++it) {
-		issue_stores(it);
-		if (!late_stores) {
-			land_stores(it);
-		} else {
-			load_tap_c(it);
+		if (late_stores) {
+			load_tap_c(it);      // loads at the point they are issued
 		}
 		if (it + 1 < nspans) {
 			run_a(it + 1);
@@ -1151,25 +1158,39 @@ inline bool emulate_stream_bulk(const MixArgs& a, int tile, int lane, bool late_
 		if (late_stores) {
 			load_tap_a(it + 2);  // issued once phase A has consumed the buffer
 		}
+		auto do_b = [&]() {
+			if (it >= 0 && it < nspans) {
+				run_b(it);
+				if (late_stores) {
+					pend_b[it & 1] = out_b;
+				} else {
+					land_b(it, out_b.data());
+				}
+			}
+		};
+		auto do_c = [&]() {
+			if (it >= 1 && it - 1 < nspans) {
+				run_c(it - 1);
+				if (late_stores) {
+					pend_c[it & 1] = out_c;
+				} else {
+					land_c(it - 1, out_c.data());
+				}
+			}
+		};
 		if ((it & 1) != 0) {
-			if (it >= 0 && it < nspans) {
-				run_b(it);
-			}
-			if (it >= 1 && it - 1 < nspans) {
-				run_c(it - 1);
-			}
+			do_b();
+			do_c();
 		} else {
-			if (it >= 1 && it - 1 < nspans) {
-				run_c(it - 1);
-			}
-			if (it >= 0 && it < nspans) {
-				run_b(it);
-			}
+			do_c();
+			do_b();
 		}
 		if (late_stores) {
-			land_stores(it);
+			// what the previous iteration issued lands now: phase B of span it - 1, phase C of span it - 2
+			land_b(it - 1, pend_b[(it - 1) & 1].data());
+			land_c(it - 2, pend_c[(it - 1) & 1].data());
 		} else {
-			load_tap_a(it + 2);
+			load_tap_a(it + 2);  // loads as late as they can land
 			load_tap_c(it);
 		}
 	}
@@ -1408,16 +1429,21 @@ __global__ void __launch_bounds__(threads(CHAIN), 1) span_kernel(const __grid_co
 // checked per coefficient block by plan_bulk_frames).  Only the chorus / flanger -- LFO-modulated positions, two reads and
 // two writes per frame -- stays on ordinary loads and stores.
 //
-// Shared memory (rows of 16 x 32 floats = 2 KB): tapC[2][18] | tapA[9] | outC[20] | outB[2][5] | staged words [3][12]
-// = 222 KB for the chain.  Per iteration `it` (B of span it):
-//   DMA lanes (serial warp 1): store outC(it-2), outB(it-1) -> rings; load tapC(it); wait until the stores have read
-//                              shared memory; arrive at barrier P; ... (own phase B) ...; wait for the stores to land
-//   parallel warps:            A(it+1) from tapA; barrier P; [warp 0: load tapA(it+2)]; C(it-1) from tapC, into outC
-//   serial warps:              B(it), main line / echo ring rows into outB
-//   everybody:                 fence.proxy.async, CTA barrier
+// Shared memory (rows of 16 x 32 floats = 2 KB): rowsC[3][20] | tapA[9] | outB[5] | staged words [3][12] = 220 KB for
+// the chain.  A phase C buffer makes one round trip per span: the copy warp fills its 18 tap rows (iteration s), phase C
+// reads them and writes its 20 store rows IN PLACE -- every element is read and written by the same thread -- (iteration
+// s + 1), the copy warp sends the rows to the rings (iteration s + 2); three buffers rotate, so nobody ever waits for a
+// buffer.  Per iteration `it` (B of span it):
+//   parallel warps:  A(it+1) from tapA; barrier P (parallel warps only); [warp 0: request tapA(it+2)]; C(it-1)
+//   serial warps:    B(it); the shelves / echo warps store their own main-line / echo rows; the T60 warp first sends
+//                    the rows of span it-2 to the rings and requests the tap rows of span it
+//   everybody:       CTA barrier
+constexpr int kBulkParallelWarps = 8;
+OALSFX_CX int bulk_threads(bool chain) { return (kBulkParallelWarps + serial_warps(chain)) * kLanes; }
+constexpr int kRowsC = 20;                // rows of one phase C buffer: 18 tap rows in, 20 store rows out, in place
 OALSFX_CX int bulk_shared_floats(bool chain)
 {
-	return (2 * tap_rows_c(chain) + tap_rows_a(chain) + kOutRowsC + 2 * out_rows_b(chain) + kBuffers * staged_words(chain)) * kBulkFrames * kLanes;
+	return (3 * kRowsC + tap_rows_a(chain) + out_rows_b(chain) + kBuffers * staged_words(chain)) * kBulkFrames * kLanes;
 }
 
 __device__ __forceinline__ unsigned shared_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
@@ -1474,20 +1500,19 @@ __device__ __forceinline__ void move_rows(bool load, float* line, int mask, int 
 }
 
 template <int CT, bool CHAIN>
-__global__ void __launch_bounds__(threads(CHAIN), 1) span_bulk_kernel(const __grid_constant__ MixArgs a)
+__global__ void __launch_bounds__(bulk_threads(CHAIN), 1) span_bulk_kernel(const __grid_constant__ MixArgs a)
 {
 	using Cx = Context<CT, CHAIN>;
-	constexpr int NS = serial_warps(CHAIN), NP = kParallelWarps, T = kBulkFrames, W = staged_words(CHAIN);
+	constexpr int NS = serial_warps(CHAIN), NP = kBulkParallelWarps, T = kBulkFrames, W = staged_words(CHAIN);
 	constexpr int RC = tap_rows_c(CHAIN), RA = tap_rows_a(CHAIN), RB = out_rows_b(CHAIN), ROW = T * kLanes;
-	constexpr int kDmaWarp = 1;                       // the T60 warp also issues the copies
-	constexpr unsigned kBarP = 1, kBarPThreads = (NP + 1) * kLanes;
+	constexpr int kCopyWarp = 1;                      // the T60 warp also moves phase C's rows
+	constexpr unsigned kBarP = 1, kBarPThreads = NP * kLanes;
 	extern __shared__ __align__(128) float dyn[];
-	float* const tap_c = dyn;                         // [2][RC][T][lane]
-	float* const tap_a = tap_c + 2 * RC * ROW;        // [RA][T][lane]
-	float* const out_c = tap_a + RA * ROW;            // [kOutRowsC][T][lane]
-	float* const out_b = out_c + kOutRowsC * ROW;     // [2][RB][T][lane]
-	float* const staged = out_b + 2 * RB * ROW;       // [3][W][T][lane]
-	__shared__ __align__(8) uint64_t mbar[3];         // tapC[0], tapC[1], tapA
+	float* const rows_c = dyn;                        // [3][kRowsC][T][lane]: taps in, store rows out
+	float* const tap_a = rows_c + 3 * kRowsC * ROW;   // [RA][T][lane]
+	float* const out_b = tap_a + RA * ROW;            // [RB][T][lane]
+	float* const staged = out_b + RB * ROW;           // [3][W][T][lane]
+	__shared__ __align__(8) uint64_t mbar[4];         // phase C buffers 0..2, tapA
 
 	const int tile = a.tiles ? static_cast<int>(a.tiles[blockIdx.x].tile) : a.tile_first + static_cast<int>(blockIdx.x);
 	const int lane = threadIdx.x % kLanes;
@@ -1505,6 +1530,7 @@ __global__ void __launch_bounds__(threads(CHAIN), 1) span_bulk_kernel(const __gr
 		mbar_init(&mbar[0], 1);
 		mbar_init(&mbar[1], 1);
 		mbar_init(&mbar[2], 1);
+		mbar_init(&mbar[3], 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	if (!__syncthreads_and(ok)) {
@@ -1519,27 +1545,25 @@ __global__ void __launch_bounds__(threads(CHAIN), 1) span_bulk_kernel(const __gr
 	float* const tile_rev = cx.ring_rev.p - lane;
 	float* const tile_echo = CHAIN ? cx.ring_echo.p - lane : nullptr;
 	auto count_of = [&](int s) { return min(T, a.frames - s * T); };
-	// one row job per lane
-	auto move = [&](bool load, const RowJob& j, int s, float* smem_row, uint64_t* bar) {
-		move_rows(load, (j.ring == 0 ? tile_rev : tile_echo) + static_cast<size_t>(j.word0) * kLanes, j.mask,
-			(j.ring == 0 ? cx.rev_off : cx.echo_off) + s * T - j.behind, count_of(s), smem_row, bar);
-	};
-	auto load_tap_a = [&](int s) {                   // whole warp; lanes 0 .. RA-1 move a row each
-		if (s < nspans) {
-			if (lane == 0) {
-				mbar_expect_tx(&mbar[2], static_cast<unsigned>(RA * count_of(s) * kLanes * 4));
-			}
-			__syncwarp();
-			if (lane < RA) {
-				move(true, tap_row_a<CHAIN>(a, lane), s, tap_a + lane * ROW, &mbar[2]);
-			}
-		}
-	};
+	auto line_of = [&](const RowJob& j) { return (j.ring == 0 ? tile_rev : tile_echo) + static_cast<size_t>(j.word0) * kLanes; };
+	auto pos_of = [&](const RowJob& j, int s) { return (j.ring == 0 ? cx.rev_off : cx.echo_off) + s * T - j.behind; };
 
 	if (w >= NS) {
 		// ---- parallel warps ----
 		const int pw = w - NS;
 		constexpr int U = T / NP;                    // frames of a span per warp: t = pw + u * NP
+		auto load_tap_a = [&](int s) {               // lanes 0 .. RA-1 move a row each
+			if (s < nspans) {
+				if (lane == 0) {
+					mbar_expect_tx(&mbar[3], static_cast<unsigned>(RA * count_of(s) * kLanes * 4));
+				}
+				__syncwarp();
+				if (lane < RA) {
+					const RowJob j = tap_row_a<CHAIN>(a, lane);
+					move_rows(true, line_of(j), j.mask, pos_of(j, s), count_of(s), tap_a + lane * ROW, &mbar[3]);
+				}
+			}
+		};
 		if (pw == 0) {
 			load_tap_a(0);
 		}
@@ -1572,14 +1596,17 @@ __global__ void __launch_bounds__(threads(CHAIN), 1) span_bulk_kernel(const __gr
 			}
 			if (it + 1 < nspans) {
 				const int s = it + 1, buf = s % kBuffers, count = count_of(s);
-				mbar_wait(&mbar[2], static_cast<unsigned>(s & 1));
+				mbar_wait(&mbar[3], static_cast<unsigned>(s & 1));
+				typename Cx::TapsA k[U];
+#pragma unroll
+				for (int u = 0; u < U; ++u) {
+					cx.template fetch_a<T, kLanes>(tap_a + (pw + u * NP) * kLanes + lane, k[u]);
+				}
 #pragma unroll
 				for (int u = 0; u < U; ++u) {
 					const int t = pw + u * NP;
 					if (t < count) {
-						typename Cx::TapsA k;
-						cx.template fetch_a<T, kLanes>(tap_a + t * kLanes + lane, k);
-						cx.phase_a(a, sg, buf, t, xa[u], k);
+						cx.phase_a(a, sg, buf, t, xa[u], k[u]);
 					}
 				}
 			}
@@ -1589,15 +1616,18 @@ __global__ void __launch_bounds__(threads(CHAIN), 1) span_bulk_kernel(const __gr
 			}
 			if (it >= 1) {
 				const int s = it - 1, buf = s % kBuffers, first = s * T, count = count_of(s);
-				mbar_wait(&mbar[s & 1], static_cast<unsigned>((s >> 1) & 1));
-				const float* rows = tap_c + (s & 1) * RC * ROW + lane;
+				mbar_wait(&mbar[s % 3], static_cast<unsigned>((s / 3) & 1));
+				float* const rows = rows_c + (s % 3) * kRowsC * ROW + lane;
+				typename Cx::TapsC k[U];
+#pragma unroll
+				for (int u = 0; u < U; ++u) {
+					cx.template fetch_c<T, kLanes>(rows + (pw + u * NP) * kLanes, k[u]);
+				}
 #pragma unroll
 				for (int u = 0; u < U; ++u) {
 					const int t = pw + u * NP;
 					if (t < count) {
-						typename Cx::TapsC k;
-						cx.template fetch_c<T, kLanes>(rows + t * kLanes, k);
-						cx.phase_c(a, sg, buf, t, first + t, xc[u], k, md[u], StageSinkC<T>{out_c + t * kLanes + lane});
+						cx.phase_c(a, sg, buf, t, first + t, xc[u], k[u], md[u], InPlaceSinkC<T>{rows + t * kLanes});
 					}
 				}
 			}
@@ -1610,7 +1640,7 @@ __global__ void __launch_bounds__(threads(CHAIN), 1) span_bulk_kernel(const __gr
 				}
 				md[u] = md_next[u];
 			}
-			fence_async_shared();
+			fence_async_shared();                    // the rows written above are copied out by the copy warp after the barrier
 			bar_all();
 		}
 		if (pw == 0) {
@@ -1624,53 +1654,63 @@ __global__ void __launch_bounds__(threads(CHAIN), 1) span_bulk_kernel(const __gr
 	}
 
 	// ---- serial warps ----
-	const StageSinkB<T> sink0 = {out_b + lane}, sink1 = {out_b + RB * ROW + lane};
-	if (w == kDmaWarp) {
+	const StageSinkB<T> sink = {out_b + lane};
+	// Phase B's own rows are stored by the warp that wrote them: before it writes them again it waits until the copies
+	// have read shared memory, at the end of every iteration until the copies of the iteration before have landed.
+	auto store_rows_b = [&](int s, int row0, int n) {
+		fence_async_shared();
+		__syncwarp();
+		if (lane < n) {
+			const RowJob j = out_row_b<CHAIN>(a, row0 + lane);
+			move_rows(false, line_of(j), j.mask, pos_of(j, s), count_of(s), out_b + (row0 + lane) * ROW, nullptr);
+		}
+	};
+	auto stores_landed_but_newest = [&]() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); };
+	if (w == kCopyWarp) {
 		T60s<2> r;
 		r.load(cx.st_rev, 0);
 		for (int it = -1; it <= nspans + 1; ++it) {
-			// rows written in the previous iteration -> rings
-			if (it - 2 >= 0 && it - 2 < nspans && lane < kOutRowsC) {
-				move(false, out_row_c<CHAIN>(a, lane), it - 2, out_c + lane * ROW, nullptr);
-			}
-			if (it - 1 >= 0 && it - 1 < nspans && lane >= kOutRowsC && lane < kOutRowsC + RB) {
-				move(false, out_row_b<CHAIN>(a, lane - kOutRowsC), it - 1, out_b + (((it - 1) & 1) * RB + lane - kOutRowsC) * ROW, nullptr);
+			bulk_wait_read();                        // buffer it % 3 has been copied out (issued an iteration ago)
+			// phase C of span it - 2 ran in the previous iteration: its 20 store rows -> rings
+			if (it - 2 >= 0 && it - 2 < nspans && lane < kRowsC) {
+				const RowJob j = out_row_c<CHAIN>(a, out_of_buffer_row(lane));
+				move_rows(false, line_of(j), j.mask, pos_of(j, it - 2), count_of(it - 2), rows_c + (((it - 2) % 3) * kRowsC + lane) * ROW, nullptr);
 			}
 			bulk_commit();
 			if (it > nspans) {
-				bulk_wait_all();
 				break;
 			}
-			// phase C's rows of span `it`, consumed in the next iteration
+			// phase C's tap rows of span `it`, consumed in the next iteration
 			if (it >= 0 && it < nspans) {
 				if (lane == 0) {
-					mbar_expect_tx(&mbar[it & 1], static_cast<unsigned>(RC * count_of(it) * kLanes * 4));
+					mbar_expect_tx(&mbar[it % 3], static_cast<unsigned>(RC * count_of(it) * kLanes * 4));
 				}
 				__syncwarp();
 				if (lane < RC) {
-					move(true, tap_row_c<CHAIN>(a, lane), it, tap_c + ((it & 1) * RC + lane) * ROW, &mbar[it & 1]);
+					const RowJob j = tap_row_c<CHAIN>(a, lane);
+					move_rows(true, line_of(j), j.mask, pos_of(j, it), count_of(it), rows_c + ((it % 3) * kRowsC + lane) * ROW, &mbar[it % 3]);
 				}
-			}
-			bulk_wait_read();                        // outC / outB may be written again
-			asm volatile("bar.arrive %0, %1;" ::"n"(kBarP), "n"(kBarPThreads) : "memory");
-			if (it >= 0 && it < nspans) {
 				r.run(c, sg, it % kBuffers, count_of(it), 0);
 			}
 			bulk_wait_all();                         // this iteration's stores have landed
-			fence_async_shared();
 			bar_all();
 		}
+		bulk_wait_all();
 		r.store(cx.st_rev, 0);
 	} else if (w == 0) {
 		Shelves<2> r;
 		r.load(cx.st_rev, 0);
 		for (int it = -1; it <= nspans; ++it) {
 			if (it >= 0 && it < nspans) {
-				r.run(c, sg, it % kBuffers, count_of(it), (it & 1) ? sink1 : sink0, 0);
+				bulk_wait_read();
+				r.run(c, sg, it % kBuffers, count_of(it), sink, 0);
+				store_rows_b(it, kOutMain, 4);
 			}
-			fence_async_shared();
+			bulk_commit();
+			stores_landed_but_newest();
 			bar_all();
 		}
+		bulk_wait_all();
 		r.store(cx.st_rev, 0);
 	} else if (CHAIN && w == 2) {
 		EqPair r;
@@ -1679,7 +1719,6 @@ __global__ void __launch_bounds__(threads(CHAIN), 1) span_bulk_kernel(const __gr
 			if (it >= 0 && it < nspans) {
 				r.run(a.slot[0].u.equalizer, sg, it % kBuffers, count_of(it));
 			}
-			fence_async_shared();
 			bar_all();
 		}
 		r.store(cx.st_eq);
@@ -1688,11 +1727,15 @@ __global__ void __launch_bounds__(threads(CHAIN), 1) span_bulk_kernel(const __gr
 		r.load(cx.st_eq, cx.st_echo);
 		for (int it = -1; it <= nspans; ++it) {
 			if (it >= 0 && it < nspans) {
-				r.run(a.slot[0].u.equalizer, a.slot[2].u.echo, sg, it % kBuffers, count_of(it), (it & 1) ? sink1 : sink0);
+				bulk_wait_read();
+				r.run(a.slot[0].u.equalizer, a.slot[2].u.echo, sg, it % kBuffers, count_of(it), sink);
+				store_rows_b(it, kOutEcho, 1);
 			}
-			fence_async_shared();
+			bulk_commit();
+			stores_landed_but_newest();
 			bar_all();
 		}
+		bulk_wait_all();
 		r.store(cx.st_eq, cx.st_echo);
 	}
 }
