@@ -416,7 +416,7 @@ struct Context {
 	}
 
 	// ---- phase C ----
-	struct TapsC { float early[4], eap[4], eline[4], lap[4], echo[2]; };
+	struct TapsC { float early[4], eap[4], eline[4], lap[4], echo[2]; float t60[4], eq[3]; };  // ring taps + phase B's results
 	struct TapsMod { float v[2]; int32_t pos; };
 
 	OALSFX_HD void load_c(const MixArgs& a, int n, TapsC& k, TapsMod& md) const
@@ -502,8 +502,25 @@ struct Context {
 		out.put(row0 + 3, f2_hi(fb));
 	}
 
-	template <class S, class Sink>
-	OALSFX_HD void phase_c(const MixArgs& a, const S& sg, int buf, int t, int n, const float* x, const TapsC& k, const TapsMod& md, const Sink& out) const
+	// phase B's results of frame t (staged words): read before any of phase C's stores, so that the frames a thread
+	// processes back to back do not wait for each other's shared-memory traffic
+	template <class S>
+	OALSFX_HD void fetch_staged(const S& sg, int buf, int t, TapsC& k) const
+	{
+		OALSFX_UNROLL
+		for (int l = 0; l < 4; ++l) {
+			k.t60[l] = sg.at(buf, kWL + l, t);
+		}
+		if (CHAIN) {
+			OALSFX_UNROLL
+			for (int q = 0; q < 3; ++q) {
+				k.eq[q] = sg.at(buf, kWQ + q, t);
+			}
+		}
+	}
+
+	template <class Sink>
+	OALSFX_HD void phase_c(const MixArgs& a, int n, const float* x, const TapsC& k, const TapsMod& md, const Sink& out) const
 	{
 		const ReverbCoef& c = a.slot[RP].u.reverb;
 		float acc[CT];
@@ -519,7 +536,7 @@ struct Context {
 			{
 				// equalizer outputs -> bus (FxEqualizer::step)
 				const EqualizerCoef& q = a.slot[0].u.equalizer;
-				const float q0 = sg.at(buf, kWQ + 0, t), q1 = sg.at(buf, kWQ + 1, t), q3 = sg.at(buf, kWQ + 2, t);
+				const float q0 = k.eq[0], q1 = k.eq[1], q3 = k.eq[2];
 				pan_add<CT, true>(acc, CT, q.gains[0], q0);
 				pan_add<CT, true>(acc, CT, q.gains[1], q1);
 				pan_add<CT, true>(acc, CT, q.gains[3], q3);
@@ -586,8 +603,8 @@ struct Context {
 			out.put(kOutFeed + 3, f2_lo(ra));
 		}
 		// late reverb after the T60 filters
-		fa = f2(sg.at(buf, kWL + 0, t), sg.at(buf, kWL + 1, t));
-		fb = f2(sg.at(buf, kWL + 2, t), sg.at(buf, kWL + 3, t));
+		fa = f2(k.t60[0], k.t60[1]);
+		fb = f2(k.t60[2], k.t60[3]);
 		allpass(c, fa, fb, k.lap, out, kOutLap);
 		out8[4] = f2_lo(fa);
 		out8[5] = f2_hi(fa);
@@ -948,8 +965,9 @@ inline bool emulate_stream(const MixArgs& a, int tile, int lane)
 			typename Cx::TapsMod md;
 			cx.load_input(a, s * T + t, x);
 			cx.load_c(a, s * T + t, k, md);
+			cx.fetch_staged(sg, s % kBuffers, t, k);
 			const RingSinkC out = {c, cx.ring_rev, cx.rev_off + s * T + t};
-			cx.phase_c(a, sg, s % kBuffers, t, s * T + t, x, k, md, out);
+			cx.phase_c(a, s * T + t, x, k, md, out);
 		}
 	};
 	for (int it = -1; it <= nspans; ++it) {
@@ -1143,8 +1161,9 @@ inline bool emulate_stream_bulk(const MixArgs& a, int tile, int lane, bool late_
 			typename Cx::TapsC k;
 			cx.load_input(a, s * T + t, x);
 			cx.template fetch_c<T, 1>(&tap_c[(s & 1) * RC * T + t], k);
+			cx.fetch_staged(sg, s % kBuffers, t, k);
 			struct Sink1 { float* base; void put(int row, float v) const { base[row * T] = v; } } out1 = {&out_c[t]};
-			cx.phase_c(a, sg, s % kBuffers, t, s * T + t, x, k, mod_taps[(s & 1) * T + t], out1);
+			cx.phase_c(a, s * T + t, x, k, mod_taps[(s & 1) * T + t], out1);
 		}
 	};
 	load_tap_a(0);
@@ -1318,13 +1337,15 @@ __global__ void __launch_bounds__(threads(CHAIN), 1) span_kernel(const __grid_co
 					typename Cx::TapsMod m0, m1;
 					cx.load_input(a, first + t, x0);
 					cx.load_c(a, first + t, k0, m0);
+					cx.fetch_staged(sg, buf, t, k0);
 					if (two) {
 						cx.load_input(a, first + t2, x1);
 						cx.load_c(a, first + t2, k1, m1);
+						cx.fetch_staged(sg, buf, t2, k1);
 					}
-					cx.phase_c(a, sg, buf, t, first + t, x0, k0, m0, RingSinkC{c, cx.ring_rev, cx.rev_off + first + t});
+					cx.phase_c(a, first + t, x0, k0, m0, RingSinkC{c, cx.ring_rev, cx.rev_off + first + t});
 					if (two) {
-						cx.phase_c(a, sg, buf, t2, first + t2, x1, k1, m1, RingSinkC{c, cx.ring_rev, cx.rev_off + first + t2});
+						cx.phase_c(a, first + t2, x1, k1, m1, RingSinkC{c, cx.ring_rev, cx.rev_off + first + t2});
 					}
 				}
 			}
@@ -1622,12 +1643,13 @@ __global__ void __launch_bounds__(bulk_threads(CHAIN), 1) span_bulk_kernel(const
 #pragma unroll
 				for (int u = 0; u < U; ++u) {
 					cx.template fetch_c<T, kLanes>(rows + (pw + u * NP) * kLanes, k[u]);
+					cx.fetch_staged(sg, buf, min(pw + u * NP, count - 1), k[u]);
 				}
 #pragma unroll
 				for (int u = 0; u < U; ++u) {
 					const int t = pw + u * NP;
 					if (t < count) {
-						cx.phase_c(a, sg, buf, t, first + t, xc[u], k[u], md[u], InPlaceSinkC<T>{rows + t * kLanes});
+						cx.phase_c(a, first + t, xc[u], k[u], md[u], InPlaceSinkC<T>{rows + t * kLanes});
 					}
 				}
 			}
