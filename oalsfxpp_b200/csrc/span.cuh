@@ -102,11 +102,12 @@ struct Legality {
 //   mr / mw  the chorus ring's reads / writes
 // span_kernel (loads and stores at the point of use):        A one iteration before B, C one after
 // span_bulk_kernel (bulk copies issued ahead, stores behind): A's rows fetched two iterations before B, C's in B's own
-//   iteration; B's row stores are issued when B is done and have landed by the end of the next iteration, C's
-//   likewise (C runs one iteration after B); the chorus taps are requested one iteration before C
+//   iteration; B's row stores are issued when B is done and have landed by the end of the next iteration; C's rows
+//   (C runs one iteration after B) are sent off at the start of the iteration after C and have landed by the end of the
+//   one after that; the chorus taps are requested one iteration before C
 struct Timing { int ra, rc, wb0, wb1, wc0, wc1, mr, mw; };
 constexpr Timing kDirectTiming = {kPhA, kPhC, kPhB, kPhB, kPhC, kPhC, kPhC, kPhC};
-constexpr Timing kBulkTiming = {-2, 0, 0, 1, 1, 2, 0, 1};
+constexpr Timing kBulkTiming = {-2, 0, 0, 1, 1, 3, 0, 1};
 constexpr int kBulkFrames = 16;           // span length of span_bulk_kernel (shared memory holds every ring row of a span)
 
 inline bool reverb_legal(const ReverbCoef& c, int t, const Timing& tm = kDirectTiming)
@@ -1134,7 +1135,7 @@ inline bool emulate_stream_bulk(const MixArgs& a, int tile, int lane, bool late_
 			}
 		}
 	};
-	std::vector<float> pend_c[2] = {std::vector<float>(kOutRowsC * T), std::vector<float>(kOutRowsC * T)};
+	std::vector<float> pend_c[3] = {std::vector<float>(kOutRowsC * T), std::vector<float>(kOutRowsC * T), std::vector<float>(kOutRowsC * T)};
 	std::vector<float> pend_b[2] = {std::vector<float>(RB * T), std::vector<float>(RB * T)};
 	auto run_a = [&](int s) {
 		for (int t = count_of(s) - 1; t >= 0; --t) {
@@ -1167,7 +1168,7 @@ inline bool emulate_stream_bulk(const MixArgs& a, int tile, int lane, bool late_
 		}
 	};
 	load_tap_a(0);
-	for (int it = -1; it <= nspans + 1; ++it) {
+	for (int it = -1; it <= nspans + 2; ++it) {
 		if (late_stores) {
 			load_tap_c(it);      // loads at the point they are issued
 		}
@@ -1191,7 +1192,7 @@ inline bool emulate_stream_bulk(const MixArgs& a, int tile, int lane, bool late_
 			if (it >= 1 && it - 1 < nspans) {
 				run_c(it - 1);
 				if (late_stores) {
-					pend_c[it & 1] = out_c;
+					pend_c[(it + 3) % 3] = out_c;
 				} else {
 					land_c(it - 1, out_c.data());
 				}
@@ -1205,9 +1206,10 @@ inline bool emulate_stream_bulk(const MixArgs& a, int tile, int lane, bool late_
 			do_b();
 		}
 		if (late_stores) {
-			// what the previous iteration issued lands now: phase B of span it - 1, phase C of span it - 2
+			// landing as late as allowed: phase B's rows of span it - 1 (issued in the previous iteration), phase C's rows
+			// of span it - 3 (produced in iteration it - 2, sent off in it - 1)
 			land_b(it - 1, pend_b[(it - 1) & 1].data());
-			land_c(it - 2, pend_c[(it - 1) & 1].data());
+			land_c(it - 3, pend_c[(it - 2 + 3) % 3].data());
 		} else {
 			load_tap_a(it + 2);  // loads as late as they can land
 			load_tap_c(it);
@@ -1688,11 +1690,24 @@ __global__ void __launch_bounds__(bulk_threads(CHAIN), 1) span_bulk_kernel(const
 		}
 	};
 	auto stores_landed_but_newest = [&]() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); };
+	// phase C's tap rows of span s -> buffer s % 3 (free: its store copies had read it before the last barrier)
+	auto request_taps_c = [&](int s) {
+		if (s >= 0 && s < nspans) {
+			if (lane == 0) {
+				mbar_expect_tx(&mbar[s % 3], static_cast<unsigned>(RC * count_of(s) * kLanes * 4));
+			}
+			__syncwarp();
+			if (lane < RC) {
+				const RowJob j = tap_row_c<CHAIN>(a, lane);
+				move_rows(true, line_of(j), j.mask, pos_of(j, s), count_of(s), rows_c + ((s % 3) * kRowsC + lane) * ROW, &mbar[s % 3]);
+			}
+		}
+	};
+	constexpr int kRequestWarp = CHAIN ? 2 : 0;       // the equalizer pair warp (chain) / the shelves warp requests phase C's taps
 	if (w == kCopyWarp) {
 		T60s<2> r;
 		r.load(cx.st_rev, 0);
 		for (int it = -1; it <= nspans + 1; ++it) {
-			bulk_wait_read();                        // buffer it % 3 has been copied out (issued an iteration ago)
 			// phase C of span it - 2 ran in the previous iteration: its 20 store rows -> rings
 			if (it - 2 >= 0 && it - 2 < nspans && lane < kRowsC) {
 				const RowJob j = out_row_c<CHAIN>(a, out_of_buffer_row(lane));
@@ -1702,19 +1717,11 @@ __global__ void __launch_bounds__(bulk_threads(CHAIN), 1) span_bulk_kernel(const
 			if (it > nspans) {
 				break;
 			}
-			// phase C's tap rows of span `it`, consumed in the next iteration
 			if (it >= 0 && it < nspans) {
-				if (lane == 0) {
-					mbar_expect_tx(&mbar[it % 3], static_cast<unsigned>(RC * count_of(it) * kLanes * 4));
-				}
-				__syncwarp();
-				if (lane < RC) {
-					const RowJob j = tap_row_c<CHAIN>(a, lane);
-					move_rows(true, line_of(j), j.mask, pos_of(j, it), count_of(it), rows_c + ((it % 3) * kRowsC + lane) * ROW, &mbar[it % 3]);
-				}
 				r.run(c, sg, it % kBuffers, count_of(it), 0);
 			}
-			bulk_wait_all();                         // this iteration's stores have landed
+			bulk_wait_read();                        // the buffer just sent off may be filled again after the barrier
+			stores_landed_but_newest();              // ... and the rows sent off one iteration ago have landed
 			bar_all();
 		}
 		bulk_wait_all();
@@ -1723,6 +1730,9 @@ __global__ void __launch_bounds__(bulk_threads(CHAIN), 1) span_bulk_kernel(const
 		Shelves<2> r;
 		r.load(cx.st_rev, 0);
 		for (int it = -1; it <= nspans; ++it) {
+			if (kRequestWarp == 0) {
+				request_taps_c(it);
+			}
 			if (it >= 0 && it < nspans) {
 				bulk_wait_read();
 				r.run(c, sg, it % kBuffers, count_of(it), sink, 0);
@@ -1738,6 +1748,7 @@ __global__ void __launch_bounds__(bulk_threads(CHAIN), 1) span_bulk_kernel(const
 		EqPair r;
 		r.load(cx.st_eq);
 		for (int it = -1; it <= nspans; ++it) {
+			request_taps_c(it);
 			if (it >= 0 && it < nspans) {
 				r.run(a.slot[0].u.equalizer, sg, it % kBuffers, count_of(it));
 			}
