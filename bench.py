@@ -7,7 +7,13 @@ equalizer + chorus + echo + EAX reverb + output interleave, fused) over ALL stre
 Workload at N=1 = BASELINE.json configs[4] on one GPU ("cfg4": 65 536 independent stereo 48 kHz
 streams, static default parameters) -- the configuration the metric and the north_star target are
 quoted on.  With N>1 every rank runs the same 65 536 streams on its own GPU (streams shard with no
-data-path collective: "weak" scaling); `value` is the whole-job aggregate.
+data-path collective: "weak" scaling); `value` is the whole-job aggregate.  The same line also carries
+  configs  cfg1 / cfg2 / cfg2 with per-block parameter changes / cfg3 of BASELINE.json on one GPU (N = 1 only):
+           ms per block, the kernel that ran, and the roofline fraction (HBM, or the FP32 issue rate for cfg3)
+  strong   (N > 1) configs[4] read literally: the 65 536 streams SHARDED over the N GPUs, with and without the
+           all-streams bus (fused per-tile sums + one pass + NCCL all-reduce) inside the timed region
+  bus      the all-streams bus at full size, as an epilogue of the mix kernel (oalsfx_engine_mix_bus)
+  e2e.link_peak   raw concurrent pinned H2D + D2H of the same bytes on the same box: the ceiling of the host-buffer path
 
   value  device-resident I/O (stream-major [stream][frame][channel] fp32 in HBM), CUDA events on the
          launching stream, max over ranks
@@ -38,6 +44,7 @@ RATE = 48000
 BLOCK = 1024
 CHAIN = (7, 1, 6, 11)  # equalizer, chorus, echo, eax_reverb (oalsfxpp::EffectType values)
 BYTES_PER_FRAME = 236  # I/O 16 + reverb rings 192 + echo 12 + chorus 16
+CFG3_OPS_PER_FRAME = 266  # dry 2 + flanger 26 + ring modulator 60 + distortion 147 + compressor 31
 METRIC = "channel-samples/s, 4-slot EAX reverb chain @48 kHz"
 UNIT = "channel-samples/s"
 
@@ -195,16 +202,115 @@ class ClockSampler:
                 "samples": len(sm), "source": "nvml" if self._nvml else "nvidia-smi"}
 
 
+# ---- the other BASELINE.json configurations (one GPU, device buffers) --------------------------------
+def secondary_configs(torch, ox, dev, stream, hbm_peak, sm_mhz):
+    """cfg1, cfg2 (static and with per-block parameter changes), cfg3: median ms per 1024-frame block (CUDA events
+    on the launching stream), the kernel the engine chose, and the roofline of each.  cfg3 is compute-bound: its
+    roofline is the FP32 issue rate (148 SMs x 128 lanes x SM clock, one non-fused operation per lane and cycle --
+    the path is compiled without FMA contraction) against 266 algorithmic operations per frame."""
+    import numpy as np
+    T = ox.EffectType
+    chain = [T.equalizer, T.chorus, T.echo, T.eax_reverb]
+
+    def run(streams, fmt, rate, effects, schedule=None, blocks=24, warm=5):
+        channels = ox.channel_count(fmt)
+        x = torch.rand(streams, BLOCK, channels, device=dev) - 0.5
+        y = torch.empty_like(x)
+        host_s, times = 0.0, []
+        with ox.Engine(streams, fmt, rate, len(effects), device=dev.index) as eng:
+            for i, t in enumerate(effects):
+                eng.set_effect(i, t)
+            for b in range(warm + blocks):
+                t0 = time.perf_counter()
+                if schedule:
+                    schedule(eng, b)
+                t1 = time.perf_counter()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                eng.mix(x, y, frames=BLOCK, stream=stream)
+                e1.record()
+                torch.cuda.synchronize()
+                if b >= warm:
+                    host_s += t1 - t0
+                    times.append(e0.elapsed_time(e1))
+            kernel = eng.last_kernel
+        return float(np.median(times)), kernel, 1e3 * host_s / blocks, streams * BLOCK
+
+    def cfg2_schedule(eng, b):  # a reverb gain ramp and an equalizer step every block, a tap change every 16 blocks
+        rv = ox.default_props(T.eax_reverb, gain_=0.20 + 0.10 * ((b % 4) / 4.0), reflections_delay_=(0.012 if (b // 16) % 2 else 0.007))
+        eq = ox.default_props(T.equalizer, mid1_gain_=1.0 + 0.5 * ((b % 8) / 8.0))
+        eng.set_effect(3, T.eax_reverb, rv)
+        eng.set_effect(0, T.equalizer, eq)
+
+    def hbm(ms, frames, bytes_per_frame):
+        achieved = bytes_per_frame * frames / (ms * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "algorithmic_bytes_per_frame": bytes_per_frame}
+
+    out = {}
+    ms, k, _, fr = run(1024, ox.ChannelFormat.mono, 48000, [T.eax_reverb])
+    out["cfg1"] = {"workload": "EAX reverb (default preset), 1024 mono 48 kHz streams", "ms_per_block": ms, "kernel": k,
+                   "roofline": hbm(ms, fr, 200)}
+    ms, k, _, fr = run(4096, ox.ChannelFormat.stereo, 48000, chain)
+    out["cfg2"] = {"workload": "equalizer+chorus+echo+EAX reverb, 4096 stereo 48 kHz streams, static parameters",
+                   "ms_per_block": ms, "kernel": k, "roofline": hbm(ms, fr, BYTES_PER_FRAME)}
+    ms, k, host_ms, fr = run(4096, ox.ChannelFormat.stereo, 48000, chain, schedule=cfg2_schedule, blocks=48)
+    out["cfg2_ramps"] = {"workload": "the same with parameter changes before every block (reverb gain ramp, equalizer step; reflections delay every 16 blocks)",
+                         "ms_per_block": ms, "kernel": k, "host_param_update_ms_per_block": host_ms, "roofline": hbm(ms, fr, BYTES_PER_FRAME)}
+    ms, k, _, fr = run(16384, ox.ChannelFormat.mono, 96000, [T.flanger, T.ring_modulator, T.distortion, T.compressor])
+    fp32_peak = 148 * 128 * (sm_mhz or 1965.0) * 1e6 / 1e12
+    achieved = CFG3_OPS_PER_FRAME * fr / (ms * 1e-3) / 1e12
+    out["cfg3"] = {"workload": "flanger+ring modulator+distortion+compressor, 16384 mono 96 kHz streams", "ms_per_block": ms, "kernel": k,
+                   "roofline": {"bound": "fp32_issue", "achieved": achieved, "peak": fp32_peak, "unit": "Tflop/s (non-fused FP32 operations)",
+                                "frac": achieved / fp32_peak, "algorithmic_ops_per_frame": CFG3_OPS_PER_FRAME,
+                                "hbm_GBps": 24 * fr / (ms * 1e-3) / 1e9}}
+    return out
+
+
+def link_peak(torch, dev, nbytes, world, dist):
+    """Raw pinned-memory copies of the e2e path's bytes, both directions at once on two streams (what a perfect
+    overlap of the host-buffer path could reach on this box)."""
+    h_in = torch.empty(nbytes // 4, dtype=torch.float32).pin_memory()
+    h_out = torch.empty(nbytes // 4, dtype=torch.float32).pin_memory()
+    d_in = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+    d_out = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    reps = 4
+
+    def once():
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+
+    once()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        once()
+    torch.cuda.synchronize()
+    secs = (time.perf_counter() - t0) / reps
+    t = torch.tensor([secs], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    secs = float(t.item())
+    return {"seconds_per_step_of_copies": secs, "h2d_plus_d2h_GBps_per_gpu": 2 * nbytes / secs / 1e9,
+            "what": f"{nbytes >> 20} MiB pinned H2D and {nbytes >> 20} MiB D2H concurrently on two streams, every rank at once, max over ranks"}
+
+
 # ---- our arm ---------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="streams per GPU (default: the cfg4 size)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-configs", action="store_true", help="leave out the cfg1 / cfg2 / cfg3 records")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -261,6 +367,7 @@ def main():
             ev[k + 1].record()
         barrier()
     launches = eng.launch_count - launches0
+    headline_kernel = eng.last_kernel  # the kernel the timed launches actually were (oalsfx_engine_last_kernel)
     total_ms = ev[0].elapsed_time(ev[-1])
     kernel_ms = sorted(ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps))
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
@@ -270,19 +377,20 @@ def main():
     value = world * S * C * F * args.steps / (total_ms_max * 1e-3)
     assert bool(torch.isfinite(y).all()), "non-finite output"
 
-    # -- the optional all-streams output bus (BASELINE config 4): per-GPU deterministic partial sum of the block
-    #    just mixed + one NCCL all-reduce of the [frames][channels] bus over NVLink.  Reported beside the headline
-    #    number, not inside its timed region (the reference has no such bus).
+    # -- the all-streams output bus (BASELINE config 4) at full size: oalsfx_engine_mix_bus = the same fused kernel with
+    #    a per-tile sum in its epilogue + one pass over [tiles][frames][channels] + (N > 1) one NCCL all-reduce of the
+    #    [frames][channels] bus over NVLink.  `extra_ms_per_block` = what the bus costs on top of the plain mix.
     bus = torch.zeros((F, C), device=dev, dtype=torch.float32)
     bus_steps = max(3, min(args.steps, 10))
 
     def step_bus():
-        eng.reduce_bus(F, y, bus, stream=stream)
+        eng.mix_bus(x, y, F, bus, stream=stream)
         if world > 1:
             dist.all_reduce(bus, op=dist.ReduceOp.SUM)
 
     step_bus()
     barrier()
+    bus_kernel = eng.last_kernel
     b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     b0.record()
     for _ in range(bus_steps):
@@ -292,10 +400,14 @@ def main():
     t = torch.tensor([b0.elapsed_time(b1) / bus_steps], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    bus_info = {"ms_per_block": float(t.item()),
-                "what": "oalsfx_engine_reduce_bus (two coalesced passes over the block's output)" +
+    bus_ms = float(t.item())
+    bus_check = float((bus.double() - (y.double().sum(dim=0) if world == 1 else bus.double())).abs().max().item())
+    bus_info = {"ms_per_block_mix_plus_bus": bus_ms, "extra_ms_per_block": bus_ms - total_ms_max / args.steps,
+                "kernel": bus_kernel,
+                "what": "oalsfx_engine_mix_bus: per-tile sums in the mix kernel's epilogue + one pass over [tiles][frames][channels]" +
                         (f" + NCCL all_reduce of [{F}][{C}] fp32 over {world} GPUs" if world > 1 else ""),
-                "bytes_read_per_gpu": S * F * C * 4}
+                "bytes_read_for_the_bus_per_gpu": ((S + 31) // 32) * F * C * 4,
+                "max_abs_diff_vs_float64_sum_of_rows": bus_check if world == 1 else None}
 
     # -- end to end through the C ABI with host buffers ---------------------------------------------------
     e2e = None
@@ -319,6 +431,55 @@ def main():
         e2e = {"value": world * S * C * F * e2e_steps / float(t.item()), "unit": UNIT,
                "h2d_bytes_per_step": S * F * C * 4, "d2h_bytes_per_step": S * F * C * 4, "steps": e2e_steps,
                "note": "oalsfx_engine_mix with pinned host buffers: H2D + kernel + D2H inside the timed region"}
+        del hx, hy, hxn, hyn
+        lp = link_peak(torch, dev, S * F * C * 4, world, dist if world > 1 else None)
+        lp["channel_samples_per_s_if_copies_were_all"] = world * S * C * F / lp["seconds_per_step_of_copies"]
+        e2e["link_peak"] = lp
+        e2e["fraction_of_link_peak"] = e2e["value"] / lp["channel_samples_per_s_if_copies_were_all"]
+
+    # -- strong scaling: BASELINE configs[4] read literally -- the 65 536 streams sharded over the N GPUs ------
+    strong = None
+    if world > 1:
+        eng.close()
+        del x, y
+        torch.cuda.empty_cache()
+        Ss = STREAMS_PER_GPU // world
+        eng = ox.Engine(Ss, CHANNEL_FORMAT, RATE, 4, device=local_rank)
+        for slot, fx in enumerate(CHAIN):
+            eng.set_effect(slot, fx)
+        x = torch.rand((Ss, F, C), device=dev, generator=gen, dtype=torch.float32) - 0.5
+        y = torch.empty_like(x)
+
+        def timed(fn):
+            for _ in range(args.warmup):
+                fn()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                fn()
+            e1.record()
+            barrier()
+            tt = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+
+        def strong_step():
+            eng.mix(x, y, frames=F, stream=stream)
+
+        def strong_step_bus():
+            eng.mix_bus(x, y, F, bus, stream=stream)
+            dist.all_reduce(bus, op=dist.ReduceOp.SUM)
+
+        ms_plain = timed(strong_step)
+        k_plain = eng.last_kernel
+        ms_bus = timed(strong_step_bus)
+        k_bus = eng.last_kernel
+        strong = {"streams_total": Ss * world, "streams_per_gpu": Ss, "ms_per_step": ms_plain, "kernel": k_plain,
+                  "value": Ss * world * C * F / (ms_plain * 1e-3), "unit": UNIT,
+                  "with_bus_in_timed_region": {"ms_per_step": ms_bus, "kernel": k_bus, "value": Ss * world * C * F / (ms_bus * 1e-3),
+                                               "what": "mix + per-GPU bus (oalsfx_engine_mix_bus) + NCCL all_reduce of the [frames][channels] bus, all inside the timed region"},
+                  "vs_one_gpu_value": None}
 
     if rank != 0:
         if world > 1:
@@ -332,26 +493,40 @@ def main():
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     median_ms = kernel_ms[len(kernel_ms) // 2]
     achieved = BYTES_PER_FRAME * S * F / (median_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_path):
-        traffic = json.load(open(traffic_path)).get("dram_bytes_per_launch")
+        tj = json.load(open(traffic_path))
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+    clock_summary = clocks.summary()
+    configs = None
+    if world == 1 and not args.skip_configs:
+        eng.close()
+        del x, y
+        torch.cuda.empty_cache()
+        configs = secondary_configs(torch, ox, dev, stream, peak, clock_summary.get("sm_mhz"))
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": workload_config(S),
+        "dtype": "f32", "data": "synthetic (uniform white noise in [-0.5, 0.5) from torch.rand -- not the hash noise of the parity tests)",
+        "config": workload_config(S),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "duo_kernel<2,FxEqualizer,FxModDelay,FxEcho,FxReverb> (kDuoChainStereo): "
-                                                    "one launch = one step = the whole fused path",
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "kernel": f"{headline_kernel} (reported by the engine after the timed launches; kDuoChainStereo = "
+                               "duo_kernel<2,FxEqualizer,FxModDelay,FxEcho,FxReverb>): one launch = one step = the whole fused path",
                      "algorithmic_bytes_per_launch": BYTES_PER_FRAME * S * F, "kernel_ms_median": median_ms,
                      "peak_source": peak_src},
-        "clocks": clocks.summary(),
+        "clocks": clock_summary,
         "gpu_launches": launches,
         "bus": bus_info,
         "device_bytes": eng.device_bytes,
     }
     if e2e is not None:
         line["e2e"] = e2e
+    if strong is not None:
+        line["strong"] = strong
+    if configs is not None:
+        line["configs"] = configs
     if world == 1 and not args.skip_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
     sys.stdout.flush()

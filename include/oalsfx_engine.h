@@ -71,6 +71,13 @@ int oalsfx_engine_set_effect(oalsfx_engine* e, int first_stream, int n_streams, 
 int oalsfx_engine_set_sends(oalsfx_engine* e, int first_stream, int n_streams,
 	const float* direct, const float* aux);
 
+/* Ordering: with device buffers oalsfx_engine_mix / mix_bus / reduce_bus / the PCM conversions are ENQUEUED on
+ * `cuda_stream` and return at once; consecutive calls on the same stream run in order.  Every other call that touches
+ * engine state on the device -- set_effect / set_sends (state reset, arena growth, table uploads at the next mix),
+ * snapshot, restore, debug_state, destroy -- first waits for the stream the caller last passed in, so it is safe to
+ * call them at any time, also with cudaStreamNonBlocking streams.  Using several streams on one engine concurrently
+ * is the caller's to order.  Precondition of the fused kernels: finite input samples (an Inf / NaN sample times a
+ * gain the reference skips as inaudible would reach output channels the reference leaves untouched). */
 /* Replaces Api::mix for all streams at once (reference: oalsfxpp.cpp:3785-3829, 2984-3037).
  * `frames` per stream; internally cut into blocks of <= 2048 frames exactly like the reference.
  * src/dst hold num_streams*frames*C floats (TILED: stream count rounded up to 32) in `space`;
@@ -84,6 +91,14 @@ int oalsfx_engine_mix(oalsfx_engine* e, int frames, const float* src, float* dst
  * engine's streams of a STREAM_MAJOR/TILED device buffer `dst` produced by oalsfx_engine_mix.
  * No reference counterpart; the cross-GPU sum is one all-reduce of `bus`. */
 int oalsfx_engine_reduce_bus(oalsfx_engine* e, int frames, const float* dst, int layout,
+	float* bus, void* cuda_stream);
+
+/* oalsfx_engine_mix (device buffers) that also delivers the all-streams bus of the block: bus[frame * C + c] = the sum
+ * of dst over the engine's streams, a device array of frames * C floats.  Where the fused kernel serves the whole
+ * engine the per-tile sums are an epilogue of the mix kernel itself (a fixed reduction tree: deterministic, the
+ * same on every run) and only [tiles][frames][C] is read back; otherwise the call is mix + reduce_bus.  Summation
+ * order differs from oalsfx_engine_reduce_bus's, i.e. the two agree to rounding (~1e-6 * sqrt(streams)), not bit for bit. */
+int oalsfx_engine_mix_bus(oalsfx_engine* e, int frames, const float* src, float* dst, int layout,
 	float* bus, void* cuda_stream);
 
 /* PCM formats either side of the path (device buffers).  The reference's only
@@ -116,6 +131,10 @@ int oalsfx_engine_debug_state(oalsfx_engine* e, int stream, int slot, int32_t ou
 
 /* How many of the engine's kernels have been launched so far (bench.py's gpu_launches). */
 long long oalsfx_engine_launch_count(const oalsfx_engine* e);
+
+/* Name of the mix kernel the engine launched most recently ("" before the first mix), e.g. "kDuoChainStereo":
+ * which of the kernel families served the last block (measurement records, tests of the selection logic). */
+const char* oalsfx_engine_last_kernel(const oalsfx_engine* e);
 
 /* Bytes of device memory the engine currently holds. */
 long long oalsfx_engine_device_bytes(const oalsfx_engine* e);

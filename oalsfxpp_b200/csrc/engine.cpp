@@ -90,7 +90,28 @@ struct oalsfx_engine {
 	std::vector<FxClass> classes;
 	std::unordered_map<std::string, int> class_index;
 	std::vector<SendClass> send_classes;
-	std::map<std::string, void*> tables; // device lookup tables by content key
+	struct Table { void* p; size_t bytes; };
+	std::map<std::string, Table> tables; // device lookup tables by content key (released when no class refers to them)
+	size_t table_bytes = 0;
+	// The stream the caller last handed to a mix / bus / PCM call: work may still be running there (a non-blocking
+	// stream does not order against the legacy NULL stream), so everything that mutates, reallocates, uploads or
+	// reads back engine state waits for it first (quiesce).
+	void* last_stream = nullptr;
+	bool stream_busy = false;
+	void note_stream(void* stream)
+	{
+		last_stream = stream;
+		stream_busy = true;
+	}
+	bool quiesce()
+	{
+		bool ok = true;
+		if (stream_busy) {
+			ok = be->sync(last_stream);
+			stream_busy = false;
+		}
+		return be->sync(nullptr) && ok;
+	}
 
 	// device arenas
 	float* ring[kMaxSlots] = {};
@@ -123,6 +144,18 @@ struct oalsfx_engine {
 	int32_t* tile_class_dev = nullptr;
 	bool groups_dirty = true;
 	long long launches = 0;
+	int last_kernel = -1;               // id of the most recent mix kernel launched (oalsfx_engine_last_kernel)
+	// oalsfx_engine_mix_bus: per-tile bus rows [tile][frame][channel] written by the fused kernel's epilogue
+	float* bus_rows = nullptr;
+	size_t bus_rows_cap = 0;            // floats
+	float* bus_rows_active = nullptr;   // non-null while a mix_bus call is in flight
+	long long bus_frames_total = 0;
+	int bus_groups = 0, bus_groups_fused = 0;
+	bool mix_launch(int id, const MixArgs& a, void* stream)
+	{
+		last_kernel = id;
+		return be->launch_mix(id, a, stream);
+	}
 	// Which fused kernel family serves whole-tile groups: 2 = automatic (default): the two-stage duo kernel,
 	// or the four-stage quartet pipeline when the group has too few tiles to fill the GPU (and for
 	// signatures that only have a quartet entry); 3 = quartet wherever it exists; 4 = duo wherever it exists;
@@ -161,11 +194,12 @@ struct oalsfx_engine {
 		}
 		be->release(stage_in);
 		be->release(stage_out);
+		be->release(bus_rows);
 		be->stream_destroy(pipe_in);
 		be->stream_destroy(pipe_run);
 		be->stream_destroy(pipe_out);
 		for (auto& kv : tables) {
-			be->release(kv.second);
+			be->release(kv.second.p);
 		}
 		delete be;
 	}
@@ -190,13 +224,14 @@ struct oalsfx_engine {
 	{
 		auto it = tables.find(key);
 		if (it != tables.end()) {
-			return it->second;
+			return it->second.p;
 		}
 		void* p = dev_alloc(bytes);
 		if (!p || !be->upload(p, data, bytes, nullptr) || !be->sync(nullptr)) {
 			return nullptr;
 		}
-		tables.emplace(key, p);
+		tables.emplace(key, Table{p, bytes});
+		table_bytes += bytes;
 		return p;
 	}
 
@@ -298,7 +333,47 @@ struct oalsfx_engine {
 			}
 		}
 		classes.swap(kept);
+		// lookup tables no surviving class points at: nothing may still be reading them
+		std::vector<const void*> live;
+		for (const FxClass& c : classes) {
+			const int kind = kind_of_type(c.type);
+			if (kind == kKindModDelay && c.coef.u.mod_delay.sin_delays) {
+				live.push_back(c.coef.u.mod_delay.sin_delays);
+			} else if (kind == kKindReverb && c.coef.u.reverb.mod_sinus) {
+				live.push_back(c.coef.u.reverb.mod_sinus);
+			}
+		}
+		bool quiet = false;
+		for (auto it = tables.begin(); it != tables.end();) {
+			if (std::find(live.begin(), live.end(), it->second.p) == live.end()) {
+				if (!quiet) {
+					quiesce();
+					quiet = true;
+				}
+				be->release(it->second.p);
+				device_bytes -= static_cast<long long>(it->second.bytes);
+				table_bytes -= it->second.bytes;
+				it = tables.erase(it);
+			} else {
+				++it;
+			}
+		}
+		// send classes no stream uses any more
+		std::vector<int> send_remap(send_classes.size(), -1);
+		std::vector<SendClass> send_kept;
+		for (int id : send_class) {
+			if (send_remap[static_cast<size_t>(id)] < 0) {
+				send_remap[static_cast<size_t>(id)] = static_cast<int>(send_kept.size());
+				send_kept.push_back(send_classes[static_cast<size_t>(id)]);
+			}
+		}
+		for (int& id : send_class) {
+			id = send_remap[static_cast<size_t>(id)];
+		}
+		send_classes.swap(send_kept);
+		compacted_at_bytes = table_bytes;
 	}
+	size_t compacted_at_bytes = 0;
 
 	int send_class_for(const SendSettings& direct, const SendSettings* aux)
 	{
@@ -433,9 +508,11 @@ struct oalsfx_engine {
 
 	bool rebuild_groups()
 	{
-		if (classes.size() > 256) {
+		// parameter automation leaves unused classes, send classes and lookup tables behind: compact by count and by bytes
+		if (classes.size() > 256 || send_classes.size() > 64 || table_bytes > compacted_at_bytes + (size_t(32) << 20)) {
 			compact_classes();
 		}
+		quiesce();  // the group tables below are uploaded in place
 		groups.clear();
 		const GroupKey k0 = key_of(0);
 		bool uniform = true;
@@ -707,6 +784,9 @@ struct oalsfx_engine {
 	bool launch_group(const Group& g, int frames, const float* src, float* dst, int layout,
 		long long frames_total, long long frame0, bool first_block, void* stream)
 	{
+		if (bus_rows_active) {
+			++bus_groups;
+		}
 		if (g.multi) {
 			MixArgs a;
 			fill_common(a, g, frames, src, dst, layout, frames_total, frame0);
@@ -729,7 +809,7 @@ struct oalsfx_engine {
 			a.class_table = class_table_dev;
 			a.tile_class = tile_class_dev;
 			++launches;
-			return be->launch_mix(multi_kernel, a, stream);
+			return mix_launch(multi_kernel, a, stream);
 		}
 		if (g.table) {
 			// key.fx[] holds the kinds; one exact single-effect pass per slot, coefficients from the tables
@@ -744,7 +824,7 @@ struct oalsfx_engine {
 				a.accumulate = first ? 0 : 1;
 				fill_slot(a, g, 0, s, first_block);
 				++launches;
-				if (!be->launch_mix(tab_kernel_for_kind(g.key.fx[s]), a, stream)) {
+				if (!mix_launch(tab_kernel_for_kind(g.key.fx[s]), a, stream)) {
 					return false;
 				}
 				first = false;
@@ -755,7 +835,7 @@ struct oalsfx_engine {
 				a.with_dry = 1;
 				fill_slot(a, g, 0, 0, first_block);
 				++launches;
-				return be->launch_mix(kTabDry, a, stream);
+				return mix_launch(kTabDry, a, stream);
 			}
 			return true;
 		}
@@ -801,7 +881,7 @@ struct oalsfx_engine {
 			a.relay_smem_floats = floats;
 			sanitize_gains(a);
 			++launches;
-			return be->launch_mix(channels == 1 ? (heavy ? kRelayMonoHeavy : kRelayMono) : (heavy ? kRelayStereoHeavy : kRelayStereo), a, stream);
+			return mix_launch(channels == 1 ? (heavy ? kRelayMonoHeavy : kRelayMono) : (heavy ? kRelayStereoHeavy : kRelayStereo), a, stream);
 		};
 		if (relay_ok && family == 5) { // OALSFX_KERNEL=relay: wherever eligible (A/B measurements, parity tests)
 			return launch_relay();
@@ -852,13 +932,13 @@ struct oalsfx_engine {
 					const int tb = span::plan_bulk_frames(a, span_chain);
 					if (tb > 0) {
 						a.span_frames = tb;
-						return be->launch_mix(span_chain ? kSpanBulkChainStereo : ki.id == kReverbMono ? kSpanBulkReverbMono : kSpanBulkReverbStereo, a, stream);
+						return mix_launch(span_chain ? kSpanBulkChainStereo : ki.id == kReverbMono ? kSpanBulkReverbMono : kSpanBulkReverbStereo, a, stream);
 					}
 				}
 				const int t = span::plan_frames(a, span_chain, kLanes >> share);
 				if (t > 0) {
 					a.span_frames = t;
-					return be->launch_mix((span_chain ? kSpanChainStereo : ki.id == kReverbMono ? kSpanReverbMono : kSpanReverbStereo) + share, a, stream);
+					return mix_launch((span_chain ? kSpanChainStereo : ki.id == kReverbMono ? kSpanReverbMono : kSpanReverbStereo) + share, a, stream);
 				}
 			}
 			// Few tiles cannot fill the GPU with two warps each: below ~one tile per SM the four-stage pipeline
@@ -872,10 +952,17 @@ struct oalsfx_engine {
 				id = quartet_for_twin(ki.id);
 			} else if (whole_tiles && family >= 2 && duo_for_twin(ki.id) >= 0) {
 				id = duo_for_twin(ki.id);
+				// the all-streams bus wanted with this mix (oalsfx_engine_mix_bus): the tile sums come out of the kernel's epilogue
+				if (bus_rows_active && g.identity && slice_count == 0 && duo_bus_for(id) >= 0) {
+					a.bus_partial = bus_rows_active + frame0 * channels;
+					a.bus_ts = bus_frames_total * channels;
+					id = duo_bus_for(id);
+					++bus_groups_fused;
+				}
 			} else if (whole_tiles && family >= 2 && quartet_for_twin(ki.id) >= 0) {
 				id = quartet_for_twin(ki.id); // no duo entry for this signature (single reverb slot)
 			}
-			return be->launch_mix(id, a, stream);
+			return mix_launch(id, a, stream);
 		}
 		if (relay_ok) {
 			return launch_relay();
@@ -894,7 +981,7 @@ struct oalsfx_engine {
 			a.accumulate = first ? 0 : 1;
 			fill_slot(a, g, 0, s, first_block);
 			++launches;
-			if (!be->launch_mix(gen_for_kind[kinds[s]], a, stream)) {
+			if (!mix_launch(gen_for_kind[kinds[s]], a, stream)) {
 				return false;
 			}
 			first = false;
@@ -904,7 +991,7 @@ struct oalsfx_engine {
 			fill_common(a, g, frames, src, dst, layout, frames_total, frame0);
 			a.with_dry = 1;
 			++launches;
-			return be->launch_mix(kGenDry, a, stream);
+			return mix_launch(kGenDry, a, stream);
 		}
 		return true;
 	}
@@ -1020,6 +1107,9 @@ int oalsfx_engine_set_effect(oalsfx_engine* e, int first_stream, int n_streams, 
 	if (id < 0) {
 		return e->fail(OALSFX_ERR_MEMORY, "Lookup table upload failed: " + e->be->error());
 	}
+	if (ring_words_for(effect_type, e->desc.sampling_rate) > e->ring_cap[slot]) {
+		e->quiesce();  // the arena is about to be copied and freed: no mix may still be running on the caller's stream
+	}
 	if (!e->ensure_ring(slot, ring_words_for(effect_type, e->desc.sampling_rate))) {
 		return e->fail(OALSFX_ERR_MEMORY, "Delay-line arena allocation failed: " + e->be->error());
 	}
@@ -1040,6 +1130,7 @@ int oalsfx_engine_set_effect(oalsfx_engine* e, int first_stream, int n_streams, 
 	}
 	if (!reset.empty()) {
 		const int n = static_cast<int>(reset.size());
+		e->quiesce();  // zeroing state a running mix may still be using
 		if (!e->be->zero_lanes(e->slot_state[slot], static_cast<long long>(kSlotStateWords) * kLanes, kSlotStateWords,
 				reset.data(), n, nullptr)) {
 			return e->fail(OALSFX_ERR_DEVICE, e->be->error());
@@ -1099,6 +1190,7 @@ int oalsfx_engine_mix(oalsfx_engine* e, int frames, const float* src, float* dst
 	const size_t count = static_cast<size_t>(padded) * static_cast<size_t>(frames) * static_cast<size_t>(e->channels);
 	const float* dsrc = src;
 	float* ddst = dst;
+	e->note_stream(cuda_stream);
 	if (space == OALSFX_SPACE_HOST) {
 		if (count > e->stage_cap) {
 			e->be->sync(cuda_stream);
@@ -1207,6 +1299,45 @@ int oalsfx_engine_mix(oalsfx_engine* e, int frames, const float* src, float* dst
 	return OALSFX_OK;
 }
 
+int oalsfx_engine_mix_bus(oalsfx_engine* e, int frames, const float* src, float* dst, int layout, float* bus, void* cuda_stream)
+{
+	if (!e || !src || !dst || !bus || frames <= 0) {
+		return e ? e->fail(OALSFX_ERR_ARGUMENT, "Bad mix_bus arguments.") : OALSFX_ERR_ARGUMENT;
+	}
+	const size_t need = static_cast<size_t>(e->tiles) * static_cast<size_t>(frames) * static_cast<size_t>(e->channels);
+	if (need > e->bus_rows_cap) {
+		e->be->sync(cuda_stream);
+		if (e->bus_rows) {
+			e->be->release(e->bus_rows);
+			e->device_bytes -= static_cast<long long>(e->bus_rows_cap) * sizeof(float);
+		}
+		e->bus_rows = static_cast<float*>(e->dev_alloc(need * sizeof(float)));
+		e->bus_rows_cap = e->bus_rows ? need : 0;
+		if (!e->bus_rows) {
+			return e->fail(OALSFX_ERR_MEMORY, "Bus row allocation failed: " + e->be->error());
+		}
+	}
+	e->bus_rows_active = e->bus_rows;
+	e->bus_frames_total = frames;
+	e->bus_groups = e->bus_groups_fused = 0;
+	const int rc = oalsfx_engine_mix(e, frames, src, dst, layout, OALSFX_SPACE_DEVICE, cuda_stream);
+	const bool fused = e->bus_groups > 0 && e->bus_groups == e->bus_groups_fused;
+	e->bus_rows_active = nullptr;
+	if (rc != OALSFX_OK) {
+		return rc;
+	}
+	if (!fused) { // some launch was not a bus-writing kernel (few tiles, heterogeneous engine ...): sum the output rows instead
+		return oalsfx_engine_reduce_bus(e, frames, dst, layout, bus, cuda_stream);
+	}
+	// the tile rows are a stream-major buffer of `tiles` "streams"
+	const long long cols = static_cast<long long>(frames) * e->channels;
+	++e->launches;
+	if (!e->be->reduce_bus(e->bus_rows, cols * kLanes, cols, e->channels, 1, e->tiles, frames, e->channels, bus, cuda_stream)) {
+		return e->fail(OALSFX_ERR_DEVICE, e->be->error());
+	}
+	return OALSFX_OK;
+}
+
 int oalsfx_engine_reduce_bus(oalsfx_engine* e, int frames, const float* dst, int layout, float* bus, void* cuda_stream)
 {
 	if (!e || !dst || !bus || frames <= 0) {
@@ -1224,6 +1355,7 @@ int oalsfx_engine_reduce_bus(oalsfx_engine* e, int frames, const float* dst, int
 		fs = e->channels;
 		cs = 1;
 	}
+	e->note_stream(cuda_stream);
 	++e->launches;
 	if (!e->be->reduce_bus(dst, ts, ls, fs, cs, e->streams, frames, e->channels, bus, cuda_stream)) {
 		return e->fail(OALSFX_ERR_DEVICE, e->be->error());
@@ -1239,6 +1371,7 @@ int oalsfx_pcm_to_float(oalsfx_engine* e, const void* src, int bit_depth, float*
 	if (bit_depth != 8 && bit_depth != 16) {
 		return e->fail(OALSFX_ERR_ARGUMENT, "Invalid bit depth."); // reference: oalsfxpp_test.cpp:738
 	}
+	e->note_stream(cuda_stream);
 	++e->launches;
 	if (!e->be->pcm_to_float(src, bit_depth, dst, count, cuda_stream)) {
 		return e->fail(OALSFX_ERR_DEVICE, e->be->error());
@@ -1252,6 +1385,7 @@ int oalsfx_float_to_s16(oalsfx_engine* e, const float* src, int16_t* dst, int ro
 	if (!e || !src || !dst || rows < 0 || row_len < 0) {
 		return e ? e->fail(OALSFX_ERR_ARGUMENT, "Bad float_to_s16 arguments.") : OALSFX_ERR_ARGUMENT;
 	}
+	e->note_stream(cuda_stream);
 	++e->launches;
 	if (!e->be->float_to_s16(src, dst, rows, row_len, row_scale, cuda_stream)) {
 		return e->fail(OALSFX_ERR_DEVICE, e->be->error());
@@ -1316,7 +1450,7 @@ int oalsfx_engine_snapshot(oalsfx_engine* e, void* dst, size_t bytes)
 	if (bytes < h.total_bytes) {
 		return e->fail(OALSFX_ERR_ARGUMENT, "Snapshot buffer too small.");
 	}
-	if (!e->be->sync(nullptr)) {
+	if (!e->quiesce()) {
 		return e->fail(OALSFX_ERR_DEVICE, e->be->error());
 	}
 	char* out = static_cast<char*>(dst);
@@ -1354,7 +1488,7 @@ int oalsfx_engine_restore(oalsfx_engine* e, const void* src, size_t bytes)
 	if (std::memcmp(&got, &want, sizeof(got)) != 0 || bytes < got.total_bytes) {
 		return e->fail(OALSFX_ERR_ARGUMENT, "Snapshot does not match this engine (streams, format, rate, slots or effect types differ).");
 	}
-	if (!e->be->sync(nullptr)) {
+	if (!e->quiesce()) {
 		return e->fail(OALSFX_ERR_DEVICE, e->be->error());
 	}
 	const char* in = static_cast<const char*>(src) + sizeof(SnapshotHeader);
@@ -1385,7 +1519,7 @@ int oalsfx_engine_debug_state(oalsfx_engine* e, int stream, int slot, int32_t ou
 	}
 	std::vector<uint32_t> words(static_cast<size_t>(kSlotStateWords) * kLanes);
 	const uint32_t* p = e->slot_state[slot] + static_cast<size_t>(stream / kLanes) * kSlotStateWords * kLanes;
-	if (!e->be->sync(nullptr) || !e->be->download(words.data(), p, words.size() * sizeof(uint32_t), nullptr) ||
+	if (!e->quiesce() || !e->be->download(words.data(), p, words.size() * sizeof(uint32_t), nullptr) ||
 		!e->be->sync(nullptr)) {
 		return e->fail(OALSFX_ERR_DEVICE, e->be->error());
 	}
@@ -1408,6 +1542,8 @@ int oalsfx_engine_debug_state(oalsfx_engine* e, int stream, int slot, int32_t ou
 }
 
 long long oalsfx_engine_launch_count(const oalsfx_engine* e) { return e ? e->launches : 0; }
+
+const char* oalsfx_engine_last_kernel(const oalsfx_engine* e) { return (e && e->last_kernel >= 0) ? kernel_name(e->last_kernel) : ""; }
 
 long long oalsfx_engine_device_bytes(const oalsfx_engine* e) { return e ? e->device_bytes : 0; }
 

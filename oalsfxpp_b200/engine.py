@@ -53,12 +53,16 @@ def bind(lib):
     lib.oalsfx_engine_set_sends.restype = i32
     lib.oalsfx_engine_mix.argtypes = [vp, i32, vp, vp, i32, i32, vp]
     lib.oalsfx_engine_mix.restype = i32
+    lib.oalsfx_engine_mix_bus.argtypes = [vp, i32, vp, vp, i32, vp, vp]
+    lib.oalsfx_engine_mix_bus.restype = i32
     lib.oalsfx_engine_reduce_bus.argtypes = [vp, i32, vp, i32, vp, vp]
     lib.oalsfx_engine_reduce_bus.restype = i32
     lib.oalsfx_engine_debug_state.argtypes = [vp, i32, i32, C.POINTER(C.c_int32)]
     lib.oalsfx_engine_debug_state.restype = i32
     lib.oalsfx_engine_launch_count.argtypes = [vp]
     lib.oalsfx_engine_launch_count.restype = C.c_longlong
+    lib.oalsfx_engine_last_kernel.argtypes = [vp]
+    lib.oalsfx_engine_last_kernel.restype = C.c_char_p
     lib.oalsfx_engine_device_bytes.argtypes = [vp]
     lib.oalsfx_engine_device_bytes.restype = C.c_longlong
     lib.oalsfx_last_error.argtypes = [vp]
@@ -88,8 +92,8 @@ def bind(lib):
 
 EXPORTED_SYMBOLS = (
     "oalsfx_engine_create", "oalsfx_engine_destroy", "oalsfx_engine_set_effect",
-    "oalsfx_engine_set_sends", "oalsfx_engine_mix", "oalsfx_engine_reduce_bus",
-    "oalsfx_engine_debug_state", "oalsfx_engine_launch_count", "oalsfx_engine_device_bytes",
+    "oalsfx_engine_set_sends", "oalsfx_engine_mix", "oalsfx_engine_mix_bus", "oalsfx_engine_reduce_bus",
+    "oalsfx_engine_debug_state", "oalsfx_engine_launch_count", "oalsfx_engine_last_kernel", "oalsfx_engine_device_bytes",
     "oalsfx_last_error", "oalsfx_build_info", "oalsfx_effect_defaults", "oalsfx_effect_normalize",
     "oalsfx_reverb_preset", "oalsfx_reverb_preset_name", "oalsfx_pcm_to_float", "oalsfx_float_to_s16",
     "oalsfx_engine_snapshot_size", "oalsfx_engine_snapshot", "oalsfx_engine_restore",
@@ -198,11 +202,20 @@ class Engine:
                 frames = src.size // (self.channels * (self.padded_streams if layout == LAYOUT_TILED else self.num_streams))
             if dst is None:
                 dst = np.empty_like(src)
+            elif not (isinstance(dst, np.ndarray) and dst.dtype == np.float32 and dst.flags["C_CONTIGUOUS"] and dst.size == src.size):
+                raise ValueError("dst must be a C-contiguous float32 array of the same size as src")
         elif frames is None:
             raise ValueError("frames is required for raw / device buffers")
         self._check(self.lib.oalsfx_engine_mix(self._h, int(frames), _ptr(src), _ptr(dst), layout, space,
                                                C.c_void_p(stream)))
         return dst
+
+    def mix_bus(self, src, dst, frames, bus, layout=LAYOUT_STREAM_MAJOR, stream=0):
+        """mix() on device buffers that also fills `bus` ([frames][channels], device) with the sum of the output over all
+        streams -- an epilogue of the fused kernel where that serves the whole engine."""
+        self._check(self.lib.oalsfx_engine_mix_bus(self._h, int(frames), _ptr(src), _ptr(dst), layout, _ptr(bus),
+                                                   C.c_void_p(stream)))
+        return bus
 
     def reduce_bus(self, frames, dst, bus, layout=LAYOUT_STREAM_MAJOR, stream=0):
         self._check(self.lib.oalsfx_engine_reduce_bus(self._h, int(frames), _ptr(dst), layout, _ptr(bus),
@@ -240,6 +253,11 @@ class Engine:
     @property
     def launch_count(self):
         return int(self.lib.oalsfx_engine_launch_count(self._h))
+
+    @property
+    def last_kernel(self):
+        """Name of the mix kernel launched most recently (which kernel family served the last block)."""
+        return self.lib.oalsfx_engine_last_kernel(self._h).decode()
 
     @property
     def device_bytes(self):

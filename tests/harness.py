@@ -40,12 +40,30 @@ def _run(cmd, **kw):
     subprocess.run(cmd, check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, **kw)
 
 
+class _BuildLock:
+    """The lazy builds below may be reached by several pytest-xdist workers at once: one builds, the others wait."""
+
+    def __enter__(self):
+        import fcntl
+        os.makedirs(os.path.join(ROOT, "tests", "_build"), exist_ok=True)
+        self._f = open(os.path.join(ROOT, "tests", "_build", ".lock"), "w")
+        fcntl.flock(self._f, fcntl.LOCK_EX)
+        return self
+
+    def __exit__(self, *exc):
+        import fcntl
+        fcntl.flock(self._f, fcntl.LOCK_UN)
+        self._f.close()
+
+
 def build_checkers():
-    _run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "all"])
+    with _BuildLock():
+        _run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "all"])
 
 
 def build_emu():
-    _run(["make", "-s", "-C", os.path.join(ROOT, "tests", "emu")])
+    with _BuildLock():
+        _run(["make", "-s", "-C", os.path.join(ROOT, "tests", "emu")])
 
 
 def _bind_orc(lib):
@@ -87,7 +105,8 @@ def ref_lib(fast=False):
 def oracle_lib():
     if "oracle" not in _CACHE:
         path = os.path.join(ROOT, "oracle", "_build", "liboalsfx_oracle.so")
-        _run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+        with _BuildLock():
+            _run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
         _CACHE["oracle"] = _bind_orc(C.CDLL(path))
     return _CACHE["oracle"]
 
@@ -125,9 +144,12 @@ def api_shim(kind):
             libdir, libname = os.path.join(ROOT, "oalsfxpp_b200"), "oalsfx_b200"
         src = os.path.join(ROOT, "oracle", "ref_shim.cpp")
         dep = os.path.join(libdir, f"lib{libname}.so")
-        if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(dep)):
-            _run(["g++", "-std=c++14", "-O2", "-fPIC", "-shared", "-pthread", "-I", os.path.join(ROOT, "include"),
-                  "-o", out, src, "-L", libdir, "-l" + libname, "-Wl,-rpath," + libdir])
+        with _BuildLock():
+            if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(dep)):
+                tmp = out + f".{os.getpid()}.tmp"
+                _run(["g++", "-std=c++14", "-O2", "-fPIC", "-shared", "-pthread", "-I", os.path.join(ROOT, "include"),
+                      "-o", tmp, src, "-L", libdir, "-l" + libname, "-Wl,-rpath," + libdir])
+                os.replace(tmp, out)
         _CACHE[key] = _bind_orc(C.CDLL(out))
     return _CACHE[key]
 

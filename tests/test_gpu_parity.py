@@ -742,6 +742,45 @@ def test_stream_major_bus_reduce_is_exact_enough_and_deterministic():
     assert bool((a == b).all())
 
 
+@pytest.mark.parametrize("streams", [7000, 96])
+def test_mix_bus_epilogue_is_the_sum_of_the_outputs(streams):
+    """oalsfx_engine_mix_bus: the all-streams bus as an epilogue of the fused chain kernel (per-tile shuffle-tree sums,
+    then one pass over [tiles][frames][channels]): the output rows are bit-identical to a plain mix, the bus equals the
+    float64 sum of the rows within 1e-5 * sqrt(S), and it is bit-identical from run to run.  7000 streams: the duo
+    kernel with a ragged last tile (the fused path); 96 streams: few tiles go to other kernels (mix + reduce_bus)."""
+    import torch
+    lib = _lib()
+    n = 512
+    chain = [T.equalizer, T.chorus, T.echo, T.eax_reverb]
+    x = torch.from_numpy(np.stack([H.noise(s % 64, 2, 2 * n) for s in range(streams)])).cuda()
+    outs = []
+    for use_bus in (False, True, True):
+        with ox.Engine(streams, F.stereo, 48000, 4, lib=lib) as eng:
+            for i, t in enumerate(chain):
+                eng.set_effect(i, t)
+            ys, buses = [], []
+            for b in range(2):
+                xb = x[:, b * n:(b + 1) * n].contiguous()
+                y = torch.empty_like(xb)
+                bus = torch.zeros(n, 2, device="cuda")
+                if use_bus:
+                    eng.mix_bus(xb, y, n, bus)
+                else:
+                    eng.mix(xb, y, frames=n)
+                torch.cuda.synchronize()
+                ys.append(y)
+                buses.append(bus)
+            kernel = eng.last_kernel
+        outs.append((torch.cat(ys, dim=1), torch.cat(buses, dim=0), kernel))
+    plain, first, second = outs
+    assert bool((plain[0] == first[0]).all()) and bool((first[0] == second[0]).all())
+    assert bool((first[1] == second[1]).all()), "the bus differs from run to run"
+    want = first[0].cpu().numpy().astype(np.float64).sum(axis=0)
+    assert np.max(np.abs(first[1].cpu().numpy() - want)) <= 1e-5 * np.sqrt(streams)
+    if streams >= 7000:
+        assert first[2] == "kDuoBusChainStereo", first[2]
+
+
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()
