@@ -12,7 +12,7 @@ data-path collective: "weak" scaling); `value` is the whole-job aggregate.  The 
            ms per block, the kernel that ran, and the roofline fraction (HBM, or the FP32 issue rate for cfg3)
   strong   (N > 1) configs[4] read literally: the 65 536 streams SHARDED over the N GPUs, with and without the
            all-streams bus (fused per-tile sums + one pass + NCCL all-reduce) inside the timed region
-  bus      the all-streams bus at full size, as an epilogue of the mix kernel (oalsfx_engine_mix_bus)
+  bus      the all-streams bus at full size (oalsfx_engine_mix_bus = mix + a deterministic reduction pass)
   e2e.link_peak   raw concurrent pinned H2D + D2H of the same bytes on the same box: the ceiling of the host-buffer path
 
   value  device-resident I/O (stream-major [stream][frame][channel] fp32 in HBM), CUDA events on the
@@ -367,6 +367,7 @@ def main():
             ev[k + 1].record()
         barrier()
     launches = eng.launch_count - launches0
+    device_bytes = eng.device_bytes
     headline_kernel = eng.last_kernel  # the kernel the timed launches actually were (oalsfx_engine_last_kernel)
     total_ms = ev[0].elapsed_time(ev[-1])
     kernel_ms = sorted(ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps))
@@ -377,9 +378,9 @@ def main():
     value = world * S * C * F * args.steps / (total_ms_max * 1e-3)
     assert bool(torch.isfinite(y).all()), "non-finite output"
 
-    # -- the all-streams output bus (BASELINE config 4) at full size: oalsfx_engine_mix_bus = the same fused kernel with
-    #    a per-tile sum in its epilogue + one pass over [tiles][frames][channels] + (N > 1) one NCCL all-reduce of the
-    #    [frames][channels] bus over NVLink.  `extra_ms_per_block` = what the bus costs on top of the plain mix.
+    # -- the all-streams output bus (BASELINE config 4) at full size: oalsfx_engine_mix_bus = mix + one deterministic pass
+    #    over the block's output + (N > 1) one NCCL all-reduce of the [frames][channels] bus over NVLink.
+    #    `extra_ms_per_block` = what the bus costs on top of the plain mix.
     bus = torch.zeros((F, C), device=dev, dtype=torch.float32)
     bus_steps = max(3, min(args.steps, 10))
 
@@ -404,9 +405,9 @@ def main():
     bus_check = float((bus.double() - (y.double().sum(dim=0) if world == 1 else bus.double())).abs().max().item())
     bus_info = {"ms_per_block_mix_plus_bus": bus_ms, "extra_ms_per_block": bus_ms - total_ms_max / args.steps,
                 "kernel": bus_kernel,
-                "what": "oalsfx_engine_mix_bus: per-tile sums in the mix kernel's epilogue + one pass over [tiles][frames][channels]" +
+                "what": "oalsfx_engine_mix_bus: mix + oalsfx_engine_reduce_bus (two coalesced passes over the block's output) on one stream" +
                         (f" + NCCL all_reduce of [{F}][{C}] fp32 over {world} GPUs" if world > 1 else ""),
-                "bytes_read_for_the_bus_per_gpu": ((S + 31) // 32) * F * C * 4,
+                "bytes_read_for_the_bus_per_gpu": S * F * C * 4,
                 "max_abs_diff_vs_float64_sum_of_rows": bus_check if world == 1 else None}
 
     # -- end to end through the C ABI with host buffers ---------------------------------------------------
@@ -519,7 +520,7 @@ def main():
         "clocks": clock_summary,
         "gpu_launches": launches,
         "bus": bus_info,
-        "device_bytes": eng.device_bytes,
+        "device_bytes": device_bytes,
     }
     if e2e is not None:
         line["e2e"] = e2e

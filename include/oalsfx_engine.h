@@ -93,11 +93,8 @@ int oalsfx_engine_mix(oalsfx_engine* e, int frames, const float* src, float* dst
 int oalsfx_engine_reduce_bus(oalsfx_engine* e, int frames, const float* dst, int layout,
 	float* bus, void* cuda_stream);
 
-/* oalsfx_engine_mix (device buffers) that also delivers the all-streams bus of the block: bus[frame * C + c] = the sum
- * of dst over the engine's streams, a device array of frames * C floats.  Where the fused kernel serves the whole
- * engine the per-tile sums are an epilogue of the mix kernel itself (a fixed reduction tree: deterministic, the
- * same on every run) and only [tiles][frames][C] is read back; otherwise the call is mix + reduce_bus.  Summation
- * order differs from oalsfx_engine_reduce_bus's, i.e. the two agree to rounding (~1e-6 * sqrt(streams)), not bit for bit. */
+/* oalsfx_engine_mix (device buffers) followed by oalsfx_engine_reduce_bus on the same stream: the block's output and
+ * bus[frame * C + c] = its sum over the engine's streams (device array of frames * C floats) from one call. */
 int oalsfx_engine_mix_bus(oalsfx_engine* e, int frames, const float* src, float* dst, int layout,
 	float* bus, void* cuda_stream);
 

@@ -147,17 +147,17 @@ __global__ void __launch_bounds__(256) float_to_s16_kernel(const float* __restri
 // one float4 column group, rows in ascending order) into partial[row group][column]; pass 2 sums the row
 // groups in ascending order.  Reads the matrix once at full HBM rate (the generic kernel above strides
 // by a whole row between threads and moves 8x the bytes).
-constexpr int kBusRows = 128;
+constexpr int kBusRows = 128;   // rows per group for tall matrices; fewer when there are few rows (see reduce_bus)
 
 __global__ void __launch_bounds__(256) bus_partial_kernel(const float* __restrict__ data, long long row_stride, int rows, int cols4,
-	float4* __restrict__ partial)
+	int group_rows, float4* __restrict__ partial)
 {
 	const int col4 = blockIdx.x * blockDim.x + threadIdx.x; // float4 column index
 	if (col4 >= cols4) {
 		return;
 	}
-	const int r0 = blockIdx.y * kBusRows;
-	const int r1 = min(r0 + kBusRows, rows);
+	const int r0 = blockIdx.y * group_rows;
+	const int r1 = min(r0 + group_rows, rows);
 	float4 acc = make_float4(0.0F, 0.0F, 0.0F, 0.0F);
 	for (int r = r0; r < r1; ++r) {
 		const float4 v = __ldcs(reinterpret_cast<const float4*>(data + r * row_stride) + col4);
@@ -333,8 +333,15 @@ public:
 		const bool rows_contiguous = cs == 1 && fs == channels && ls == cols && ts == ls * kLanes && cols % 4 == 0 &&
 			((reinterpret_cast<unsigned long long>(data) | reinterpret_cast<unsigned long long>(bus)) & 15ULL) == 0;
 		if (rows_contiguous) {
-			const int groups = (num_streams + kBusRows - 1) / kBusRows;
 			const int cols4 = static_cast<int>(cols / 4);
+			const unsigned gx = static_cast<unsigned>((cols4 + 255) / 256);
+			// Rows per group: 128 for tall matrices; with few rows (the per-tile bus rows of mix_bus: one row per 32 streams)
+			// fewer, so that pass 1 still fills the GPU (~4 CTAs per SM).  A function of the shape only: deterministic.
+			int group_rows = kBusRows;
+			while (group_rows > 4 && static_cast<long long>((num_streams + group_rows - 1) / group_rows) * gx < 592) {
+				group_rows /= 2;
+			}
+			const int groups = (num_streams + group_rows - 1) / group_rows;
 			const size_t need = static_cast<size_t>(groups) * static_cast<size_t>(cols) * sizeof(float);
 			if (need > bus_partial_bytes_) {
 				cudaFree(bus_partial_);
@@ -345,8 +352,7 @@ public:
 				}
 				bus_partial_bytes_ = need;
 			}
-			const unsigned gx = static_cast<unsigned>((cols4 + 255) / 256);
-			bus_partial_kernel<<<dim3(gx, static_cast<unsigned>(groups)), 256, 0, st>>>(data, ls, num_streams, cols4,
+			bus_partial_kernel<<<dim3(gx, static_cast<unsigned>(groups)), 256, 0, st>>>(data, ls, num_streams, cols4, group_rows,
 				static_cast<float4*>(bus_partial_));
 			bus_final_kernel<<<static_cast<unsigned>((cols4 + 31) / 32), 256, 0, st>>>(static_cast<const float4*>(bus_partial_), groups, cols4,
 				reinterpret_cast<float4*>(bus));

@@ -89,10 +89,7 @@ __device__ __forceinline__ void store_passthrough_history(uint32_t* ss, int send
 	}
 }
 
-// BUS: the back warp also reduces every finished frame over the tile's 32 streams (xor-shuffle tree, the same order for
-// every tile and launch) and writes one row per tile -- the all-streams output bus then needs a pass over
-// [tiles][frames][channels] instead of re-reading the whole [streams][frames][channels] output.
-template <int CT, class F0, class F1, class F2, class F3, bool BUS = false>
+template <int CT, class F0, class F1, class F2, class F3>
 __device__ __forceinline__ void duo_body(const MixArgs& a)
 {
 	// A reverb in slot 3 is split: its input stage (B->A conversion, shelf filters, main-line feed,
@@ -278,19 +275,6 @@ __device__ __forceinline__ void duo_body(const MixArgs& a)
 				} else {
 					r3.step(a, 3, x, acc);
 				}
-				if (BUS) {
-#pragma unroll
-					for (int c = 0; c < CT; ++c) {
-						float v = io_ok ? acc[c] : 0.0F;
-#pragma unroll
-						for (int o = kLanes / 2; o > 0; o >>= 1) {
-							v += __shfl_xor_sync(0xFFFFFFFFU, v, o);
-						}
-						if (lane == 0) {
-							a.bus_partial[tile * a.bus_ts + static_cast<long long>(i) * CT + c] = v;
-						}
-					}
-				}
 				if (fast_out) {
 #pragma unroll
 					for (int c = 0; c < CT; ++c) {
@@ -335,13 +319,6 @@ __global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_kernel(
 	const __grid_constant__ MixArgs a)
 {
 	duo_body<CT, F0, F1, F2, F3>(a);
-}
-
-// The same with the per-tile bus rows (MixArgs::bus_partial).
-template <int CT, class F0, class F1, class F2, class F3>
-__global__ void __launch_bounds__(64, OALSFX_DUO_MIN_CTAS) duo_bus_kernel(const __grid_constant__ MixArgs a)
-{
-	duo_body<CT, F0, F1, F2, F3, true>(a);
 }
 
 // One parameter class PER TILE (every stream block of 32 its own presets): the launch-wide part of the arguments

@@ -145,12 +145,7 @@ struct oalsfx_engine {
 	bool groups_dirty = true;
 	long long launches = 0;
 	int last_kernel = -1;               // id of the most recent mix kernel launched (oalsfx_engine_last_kernel)
-	// oalsfx_engine_mix_bus: per-tile bus rows [tile][frame][channel] written by the fused kernel's epilogue
-	float* bus_rows = nullptr;
-	size_t bus_rows_cap = 0;            // floats
-	float* bus_rows_active = nullptr;   // non-null while a mix_bus call is in flight
-	long long bus_frames_total = 0;
-	int bus_groups = 0, bus_groups_fused = 0;
+
 	bool mix_launch(int id, const MixArgs& a, void* stream)
 	{
 		last_kernel = id;
@@ -194,7 +189,6 @@ struct oalsfx_engine {
 		}
 		be->release(stage_in);
 		be->release(stage_out);
-		be->release(bus_rows);
 		be->stream_destroy(pipe_in);
 		be->stream_destroy(pipe_run);
 		be->stream_destroy(pipe_out);
@@ -784,9 +778,6 @@ struct oalsfx_engine {
 	bool launch_group(const Group& g, int frames, const float* src, float* dst, int layout,
 		long long frames_total, long long frame0, bool first_block, void* stream)
 	{
-		if (bus_rows_active) {
-			++bus_groups;
-		}
 		if (g.multi) {
 			MixArgs a;
 			fill_common(a, g, frames, src, dst, layout, frames_total, frame0);
@@ -952,13 +943,7 @@ struct oalsfx_engine {
 				id = quartet_for_twin(ki.id);
 			} else if (whole_tiles && family >= 2 && duo_for_twin(ki.id) >= 0) {
 				id = duo_for_twin(ki.id);
-				// the all-streams bus wanted with this mix (oalsfx_engine_mix_bus): the tile sums come out of the kernel's epilogue
-				if (bus_rows_active && g.identity && slice_count == 0 && duo_bus_for(id) >= 0) {
-					a.bus_partial = bus_rows_active + frame0 * channels;
-					a.bus_ts = bus_frames_total * channels;
-					id = duo_bus_for(id);
-					++bus_groups_fused;
-				}
+
 			} else if (whole_tiles && family >= 2 && quartet_for_twin(ki.id) >= 0) {
 				id = quartet_for_twin(ki.id); // no duo entry for this signature (single reverb slot)
 			}
@@ -1304,38 +1289,12 @@ int oalsfx_engine_mix_bus(oalsfx_engine* e, int frames, const float* src, float*
 	if (!e || !src || !dst || !bus || frames <= 0) {
 		return e ? e->fail(OALSFX_ERR_ARGUMENT, "Bad mix_bus arguments.") : OALSFX_ERR_ARGUMENT;
 	}
-	const size_t need = static_cast<size_t>(e->tiles) * static_cast<size_t>(frames) * static_cast<size_t>(e->channels);
-	if (need > e->bus_rows_cap) {
-		e->be->sync(cuda_stream);
-		if (e->bus_rows) {
-			e->be->release(e->bus_rows);
-			e->device_bytes -= static_cast<long long>(e->bus_rows_cap) * sizeof(float);
-		}
-		e->bus_rows = static_cast<float*>(e->dev_alloc(need * sizeof(float)));
-		e->bus_rows_cap = e->bus_rows ? need : 0;
-		if (!e->bus_rows) {
-			return e->fail(OALSFX_ERR_MEMORY, "Bus row allocation failed: " + e->be->error());
-		}
-	}
-	e->bus_rows_active = e->bus_rows;
-	e->bus_frames_total = frames;
-	e->bus_groups = e->bus_groups_fused = 0;
+	// One pass over the block's output right behind the mix, on the same stream.  (Summing inside the fused kernel's
+	// epilogue -- per-tile shuffle trees in its back warp, in one go, spread over the next hand-off, or in a third warp --
+	// was measured at +0.21 / +0.35 / +0.57 ms per 65 536-stream block against 0.10 ms for this pass: that warp is the
+	// kernel's critical path.  profiles/r02_history.md.)
 	const int rc = oalsfx_engine_mix(e, frames, src, dst, layout, OALSFX_SPACE_DEVICE, cuda_stream);
-	const bool fused = e->bus_groups > 0 && e->bus_groups == e->bus_groups_fused;
-	e->bus_rows_active = nullptr;
-	if (rc != OALSFX_OK) {
-		return rc;
-	}
-	if (!fused) { // some launch was not a bus-writing kernel (few tiles, heterogeneous engine ...): sum the output rows instead
-		return oalsfx_engine_reduce_bus(e, frames, dst, layout, bus, cuda_stream);
-	}
-	// the tile rows are a stream-major buffer of `tiles` "streams"
-	const long long cols = static_cast<long long>(frames) * e->channels;
-	++e->launches;
-	if (!e->be->reduce_bus(e->bus_rows, cols * kLanes, cols, e->channels, 1, e->tiles, frames, e->channels, bus, cuda_stream)) {
-		return e->fail(OALSFX_ERR_DEVICE, e->be->error());
-	}
-	return OALSFX_OK;
+	return rc != OALSFX_OK ? rc : oalsfx_engine_reduce_bus(e, frames, dst, layout, bus, cuda_stream);
 }
 
 int oalsfx_engine_reduce_bus(oalsfx_engine* e, int frames, const float* dst, int layout, float* bus, void* cuda_stream)

@@ -20,13 +20,6 @@ bool launch_duo_family(int kernel_id, const MixArgs& args, cudaStream_t st)
 		return true; }
 		OALSFX_DUO_TABLE(OALSFX_DX)
 #undef OALSFX_DX
-#define OALSFX_DBX(id, CT, F0, F1, F2, F3, duo_id) \
-	case id: { \
-		const size_t dyn = prefer_shared(done[id], duo::duo_bus_kernel<CT, F0, F1, F2, F3>, 50); \
-		duo::duo_bus_kernel<CT, F0, F1, F2, F3><<<static_cast<unsigned>(args.tile_count), 64, dyn, st>>>(args); \
-		return true; }
-		OALSFX_DUO_BUS_TABLE(OALSFX_DBX)
-#undef OALSFX_DBX
 #define OALSFX_MX(id, CT, F0, F1, F2, F3, duo_id) \
 	case id: { \
 		const size_t dyn = prefer_shared(done[id], duo::duo_multi_kernel<CT, F0, F1, F2, F3>, 50); \

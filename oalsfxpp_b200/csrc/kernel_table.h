@@ -38,10 +38,6 @@
 #define OALSFX_DUO_TABLE(DX) \
 	DX(kDuoChainStereo, 2, FxEqualizer, FxModDelay, FxEcho, FxReverb, kChainStereo)
 
-// Duo kernels that also write every tile's bus row (duo_bus_kernel).  DBX(id, CT, F0, F1, F2, F3, duo id with the same signature).
-#define OALSFX_DUO_BUS_TABLE(DBX) \
-	DBX(kDuoBusChainStereo, 2, FxEqualizer, FxModDelay, FxEcho, FxReverb, kDuoChainStereo)
-
 // Class-per-tile duo kernels (duo_multi_kernel): MX(id, CT, F0, F1, F2, F3, duo id with the same signature).
 #define OALSFX_MULTI_TABLE(MX) \
 	MX(kMultiChainStereo, 2, FxEqualizer, FxModDelay, FxEcho, FxReverb, kDuoChainStereo)
@@ -131,9 +127,6 @@ enum KernelId : int {
 #define OALSFX_MX(id, CT, F0, F1, F2, F3, duo) id,
 	OALSFX_MULTI_TABLE(OALSFX_MX)
 #undef OALSFX_MX
-#define OALSFX_DBX(id, CT, F0, F1, F2, F3, duo) id,
-	OALSFX_DUO_BUS_TABLE(OALSFX_DBX)
-#undef OALSFX_DBX
 	kKernelEnd
 };
 
@@ -143,15 +136,6 @@ inline int quartet_for_twin(int twin_id)
 #define OALSFX_TX(id, CT, F0, F1, F2, F3, twin) if (twin_id == twin) return id;
 	OALSFX_QUARTET_TABLE(OALSFX_TX)
 #undef OALSFX_TX
-	return -1;
-}
-
-// bus-writing variant of a duo kernel id, or -1
-inline int duo_bus_for(int duo_id)
-{
-#define OALSFX_DBX(id, CT, F0, F1, F2, F3, duo) if (duo_id == duo) return id;
-	OALSFX_DUO_BUS_TABLE(OALSFX_DBX)
-#undef OALSFX_DBX
 	return -1;
 }
 
@@ -257,9 +241,6 @@ inline const char* kernel_name(int id)
 #define OALSFX_MX(mid, CT, F0, F1, F2, F3, duo) if (id == mid) return #mid;
 	OALSFX_MULTI_TABLE(OALSFX_MX)
 #undef OALSFX_MX
-#define OALSFX_DBX(bid, CT, F0, F1, F2, F3, duo) if (id == bid) return #bid;
-	OALSFX_DUO_BUS_TABLE(OALSFX_DBX)
-#undef OALSFX_DBX
 	return "?";
 }
 

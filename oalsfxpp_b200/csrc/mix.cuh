@@ -69,10 +69,6 @@ struct MixArgs {
 	// Class-per-tile kernels (duo_multi_kernel): tile t runs with class_table[tile_class[t]]
 	const struct MixClassEntry* class_table;
 	const int32_t* tile_class;
-	// Bus-producing kernels (duo_bus_kernel): besides the output rows, every tile's sum over its 32 streams goes to
-	// bus_partial[tile * bus_ts + frame * channels + c] (a fixed shuffle tree: deterministic)
-	float* bus_partial;
-	long long bus_ts;
 };
 
 // The per-class part of MixArgs: direct, aux[], slot[] (contiguous), plus the class's pending-update bits.

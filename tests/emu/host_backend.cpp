@@ -118,25 +118,6 @@ public:
 			}
 			return true;
 		}
-		// a bus-writing duo kernel: its twin, then every tile's row of sums
-#define OALSFX_DBX(id, CT, F0, F1, F2, F3, duo) if (kernel_id == id) { \
-			MixArgs t = a; t.bus_partial = nullptr; \
-			if (!launch_mix(duo, t, stream)) { return false; } \
-			for (int w = 0; w < a.tile_count; ++w) { \
-				const int tile = a.tiles ? static_cast<int>(a.tiles[w].tile) : a.tile_first + w; \
-				for (int i = 0; i < a.frames; ++i) { \
-					for (int ch = 0; ch < CT; ++ch) { \
-						float sum = 0.0F; \
-						for (int lane = 0; lane < kLanes; ++lane) { \
-							if (tile * kLanes + lane < a.num_streams) { sum += a.dst[tile * a.io_ts + lane * a.io_ls + i * a.io_fs + ch * a.io_cs]; } \
-						} \
-						a.bus_partial[tile * a.bus_ts + static_cast<long long>(i) * CT + ch] = sum; \
-					} \
-				} \
-			} \
-			return true; }
-		OALSFX_DUO_BUS_TABLE(OALSFX_DBX)
-#undef OALSFX_DBX
 		int span_twin = -1;
 #define OALSFX_SX(id, CT, SL, CHAIN) if (kernel_id == id) { span_twin = (CHAIN ? kChainStereo : CT == 1 ? kReverbMono : kReverbStereo); }
 		OALSFX_SPAN_TABLE(OALSFX_SX)
