@@ -432,7 +432,30 @@ def main():
         e2e = {"value": world * S * C * F * e2e_steps / float(t.item()), "unit": UNIT,
                "h2d_bytes_per_step": S * F * C * 4, "d2h_bytes_per_step": S * F * C * 4, "steps": e2e_steps,
                "note": "oalsfx_engine_mix with pinned host buffers: H2D + kernel + D2H inside the timed region"}
-        del hx, hy, hxn, hyn
+        # the same call with the caller's buffers as an unmodified host program would have them (pageable, from the C
+        # allocator), and after oalsfx_engine_pin_host has page-locked them in place
+        def e2e_rate(a_in, a_out, steps):
+            eng.mix(a_in, a_out, frames=F)
+            barrier()
+            t_0 = time.perf_counter()
+            for _ in range(steps):
+                eng.mix(a_in, a_out, frames=F)
+            barrier()
+            tt = torch.tensor([time.perf_counter() - t_0], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return world * S * C * F * steps / float(tt.item())
+
+        px = np.array(hxn, copy=True)
+        py = np.empty_like(px)
+        e2e["pageable_buffers"] = {"value": e2e_rate(px, py, 3), "unit": UNIT}
+        eng.pin_host(px)
+        eng.pin_host(py)
+        e2e["pageable_buffers_after_pin_host"] = {"value": e2e_rate(px, py, 5), "unit": UNIT,
+                                                  "note": "oalsfx_engine_pin_host (cudaHostRegister in place); OALSFX_PIN_HOST=1 does it on first sight"}
+        eng.unpin_host(px)
+        eng.unpin_host(py)
+        del hx, hy, hxn, hyn, px, py
         lp = link_peak(torch, dev, S * F * C * 4, world, dist if world > 1 else None)
         lp["channel_samples_per_s_if_copies_were_all"] = world * S * C * F / lp["seconds_per_step_of_copies"]
         e2e["link_peak"] = lp

@@ -93,6 +93,15 @@ int oalsfx_engine_mix(oalsfx_engine* e, int frames, const float* src, float* dst
 int oalsfx_engine_reduce_bus(oalsfx_engine* e, int frames, const float* dst, int layout,
 	float* bus, void* cuda_stream);
 
+/* Host buffers: oalsfx_engine_mix with OALSFX_SPACE_HOST copies at the pinned rate (and overlaps copies with kernels)
+ * only from page-locked memory; pageable memory (malloc, new, std::vector) goes through the driver's bounce buffers at a
+ * fraction of it.  oalsfx_engine_pin_host page-locks a caller's buffer IN PLACE (cudaHostRegister) until
+ * oalsfx_engine_unpin_host or oalsfx_engine_destroy; the buffer must stay allocated for that long.  With the environment
+ * variable OALSFX_PIN_HOST=1 the engine does this by itself for every host buffer it is handed (same lifetime rule:
+ * do not free or unmap such a buffer while the engine lives; moving or resizing is detected by address overlap). */
+int oalsfx_engine_pin_host(oalsfx_engine* e, void* buffer, size_t bytes);
+int oalsfx_engine_unpin_host(oalsfx_engine* e, void* buffer);
+
 /* oalsfx_engine_mix (device buffers) followed by oalsfx_engine_reduce_bus on the same stream: the block's output and
  * bus[frame * C + c] = its sum over the engine's streams (device array of frames * C floats) from one call. */
 int oalsfx_engine_mix_bus(oalsfx_engine* e, int frames, const float* src, float* dst, int layout,

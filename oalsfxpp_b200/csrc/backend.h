@@ -29,6 +29,9 @@ public:
 	virtual bool zero(void* p, size_t bytes, void* stream) = 0;
 	virtual bool upload(void* dst, const void* src, size_t bytes, void* stream) = 0;
 	virtual bool download(void* dst, const void* src, size_t bytes, void* stream) = 0;
+	// Page-lock / release a caller's host buffer (no-ops in the CPU test backend).
+	virtual bool host_register(void*, size_t) { return true; }
+	virtual void host_unregister(void*) {}
 	// dst/src are device pointers; rows of `width` bytes.
 	virtual bool copy_2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width, size_t rows,
 		void* stream) = 0;

@@ -58,11 +58,11 @@ __global__ void reduce_bus_kernel(const float* data, long long ts, long long ls,
 
 // ---- PCM formats either side of the path ---------------------------------------
 // HBM-bound element-wise kernels: 16-byte accesses, grid-stride over a multiple of the SM count.
-__global__ void __launch_bounds__(256) pcm16_to_float_kernel(const int16_t* __restrict__ src, float* __restrict__ dst, long long count)
+__global__ void __launch_bounds__(256) pcm16_to_float_kernel(const int16_t* __restrict__ src, float* __restrict__ dst, long long count, bool vector_ok)
 {
 	// reference: oalsfxpp_test.cpp:728-733  dst[i] = little(src[i]) / 32768.0F
 	const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-	const long long vec = count / 8;
+	const long long vec = vector_ok ? count / 8 : 0;   // 16-byte accesses need 16-byte aligned buffers
 	for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < vec; i += stride) {
 		const int4 raw = __ldcs(reinterpret_cast<const int4*>(src) + i);
 		const int w[4] = {raw.x, raw.y, raw.z, raw.w};
@@ -81,11 +81,11 @@ __global__ void __launch_bounds__(256) pcm16_to_float_kernel(const int16_t* __re
 	}
 }
 
-__global__ void __launch_bounds__(256) pcm8_to_float_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, long long count)
+__global__ void __launch_bounds__(256) pcm8_to_float_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, long long count, bool vector_ok)
 {
 	// reference: oalsfxpp_test.cpp:714-719  dst[i] = (int(src[i]) - 128) / 128.0F
 	const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-	const long long vec = count / 4;
+	const long long vec = vector_ok ? count / 4 : 0;
 	for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < vec; i += stride) {
 		const unsigned raw = __ldcs(reinterpret_cast<const unsigned*>(src) + i);
 		float4 o;
@@ -219,10 +219,31 @@ public:
 	}
 
 	bool bind() { return check(cudaSetDevice(device_), "cudaSetDevice"); }
+	// Every entry point runs on the engine's device and leaves the calling thread's current device as it found it
+	// (a host process with several GPUs keeps its own notion of "current").
+	struct DeviceScope {
+		int previous = -1;
+		bool ok;
+		explicit DeviceScope(CudaBackend* be)
+		{
+			cudaGetDevice(&previous);
+			ok = previous == be->device_ || be->bind();
+			if (previous == be->device_) {
+				previous = -1;
+			}
+		}
+		~DeviceScope()
+		{
+			if (previous >= 0) {
+				cudaSetDevice(previous);
+			}
+		}
+	};
 
 	void* alloc(size_t bytes) override
 	{
-		if (!bind()) {
+		DeviceScope scope(this);
+		if (!scope.ok) {
 			return nullptr;
 		}
 		void* p = nullptr;
@@ -245,32 +266,59 @@ public:
 
 	bool zero(void* p, size_t bytes, void* stream) override
 	{
-		return bind() && check(cudaMemsetAsync(p, 0, bytes, static_cast<cudaStream_t>(stream)), "cudaMemsetAsync");
+		DeviceScope scope(this);
+		return scope.ok && check(cudaMemsetAsync(p, 0, bytes, static_cast<cudaStream_t>(stream)), "cudaMemsetAsync");
 	}
 
 	bool upload(void* dst, const void* src, size_t bytes, void* stream) override
 	{
-		return bind() && check(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)),
+		DeviceScope scope(this);
+		return scope.ok && check(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)),
 			"cudaMemcpyAsync(H2D)");
 	}
 
 	bool download(void* dst, const void* src, size_t bytes, void* stream) override
 	{
-		return bind() && check(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)),
+		DeviceScope scope(this);
+		return scope.ok && check(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)),
 			"cudaMemcpyAsync(D2H)");
+	}
+
+	// Page-lock a caller's host buffer in place so that copies to / from it run at the pinned rate and overlap with kernels.
+	// Already page-locked memory (cudaHostAlloc, torch pin_memory) is fine and reported as success.
+	bool host_register(void* p, size_t bytes) override
+	{
+		DeviceScope scope(this);
+		if (!scope.ok) {
+			return false;
+		}
+		const cudaError_t err = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+		if (err == cudaErrorHostMemoryAlreadyRegistered) {
+			cudaGetLastError();
+			return true;
+		}
+		return check(err, "cudaHostRegister");
+	}
+	void host_unregister(void* p) override
+	{
+		if (cudaHostUnregister(p) != cudaSuccess) {
+			cudaGetLastError();
+		}
 	}
 
 	bool copy_2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width, size_t rows,
 		void* stream) override
 	{
-		return bind() && check(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width, rows, cudaMemcpyDeviceToDevice,
+		DeviceScope scope(this);
+		return scope.ok && check(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width, rows, cudaMemcpyDeviceToDevice,
 			static_cast<cudaStream_t>(stream)), "cudaMemcpy2DAsync");
 	}
 
 	bool zero_lanes(uint32_t* base, long long tile_stride, int words, const TileRef* tiles, int n_tiles,
 		void* stream) override
 	{
-		if (!bind()) {
+		DeviceScope scope(this);
+		if (!scope.ok) {
 			return false;
 		}
 		if (n_tiles <= 0 || words <= 0) {
@@ -286,12 +334,19 @@ public:
 			return check(cudaMemsetAsync(base + static_cast<long long>(tiles[0].tile) * tile_stride, 0,
 				static_cast<size_t>(n_tiles) * static_cast<size_t>(tile_stride) * sizeof(uint32_t), st), "cudaMemsetAsync");
 		}
-		TileRef* dev_tiles = nullptr;
-		if (!check(cudaMalloc(&dev_tiles, static_cast<size_t>(n_tiles) * sizeof(TileRef)), "cudaMalloc")) {
-			return false;
+		// the tile list lives in a buffer that is kept and grown on demand (no allocation per call)
+		const size_t need = static_cast<size_t>(n_tiles) * sizeof(TileRef);
+		if (need > zero_tiles_bytes_) {
+			cudaFree(zero_tiles_);
+			zero_tiles_ = nullptr;
+			zero_tiles_bytes_ = 0;
+			if (!check(cudaMalloc(&zero_tiles_, need), "cudaMalloc(zero_lanes tile list)")) {
+				return false;
+			}
+			zero_tiles_bytes_ = need;
 		}
-		bool ok = check(cudaMemcpyAsync(dev_tiles, tiles, static_cast<size_t>(n_tiles) * sizeof(TileRef),
-			cudaMemcpyHostToDevice, st), "cudaMemcpyAsync");
+		TileRef* dev_tiles = static_cast<TileRef*>(zero_tiles_);
+		bool ok = check(cudaMemcpyAsync(dev_tiles, tiles, need, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync");
 		if (ok) {
 			for (int first = 0; first < n_tiles && ok; first += 65535) {
 				const int n = (n_tiles - first < 65535 ? n_tiles - first : 65535);
@@ -301,14 +356,14 @@ public:
 				ok = check(cudaGetLastError(), "zero_lanes_kernel");
 			}
 		}
-		ok = check(cudaStreamSynchronize(st), "cudaStreamSynchronize") && ok;
-		cudaFree(dev_tiles);
-		return ok;
+		// the host array may go away and the list buffer be rewritten by the next call
+		return check(cudaStreamSynchronize(st), "cudaStreamSynchronize") && ok;
 	}
 
 	bool launch_mix(int kernel_id, const MixArgs& args, void* stream) override
 	{
-		if (!bind()) {
+		DeviceScope scope(this);
+		if (!scope.ok) {
 			return false;
 		}
 		cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -325,7 +380,8 @@ public:
 	bool reduce_bus(const float* data, long long ts, long long ls, long long fs, long long cs,
 		int num_streams, int frames, int channels, float* bus, void* stream) override
 	{
-		if (!bind()) {
+		DeviceScope scope(this);
+		if (!scope.ok) {
 			return false;
 		}
 		cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -365,7 +421,8 @@ public:
 
 	bool pcm_to_float(const void* src, int bits, float* dst, long long count, void* stream) override
 	{
-		if (!bind()) {
+		DeviceScope scope(this);
+		if (!scope.ok) {
 			return false;
 		}
 		if (count <= 0) {
@@ -376,10 +433,12 @@ public:
 		const long long want = (count / 8 + 255) / 256;
 		const unsigned blocks = static_cast<unsigned>(want < 1 ? 1 : want > 8LL * sms ? 8LL * sms : want);
 		cudaStream_t st = static_cast<cudaStream_t>(stream);
+		// a payload behind a 44-byte WAV header, a tensor slice ...: misaligned buffers take the scalar loop
+		const bool aligned = ((reinterpret_cast<unsigned long long>(src) | reinterpret_cast<unsigned long long>(dst)) & 15ULL) == 0;
 		if (bits == 16) {
-			pcm16_to_float_kernel<<<blocks, 256, 0, st>>>(static_cast<const int16_t*>(src), dst, count);
+			pcm16_to_float_kernel<<<blocks, 256, 0, st>>>(static_cast<const int16_t*>(src), dst, count, aligned);
 		} else if (bits == 8) {
-			pcm8_to_float_kernel<<<blocks, 256, 0, st>>>(static_cast<const uint8_t*>(src), dst, count);
+			pcm8_to_float_kernel<<<blocks, 256, 0, st>>>(static_cast<const uint8_t*>(src), dst, count, aligned);
 		} else {
 			error_ = "Invalid bit depth."; // the reference's message (oalsfxpp_test.cpp:738)
 			return false;
@@ -389,7 +448,8 @@ public:
 
 	bool float_to_s16(const float* src, int16_t* dst, int rows, long long row_len, float* row_scale, void* stream) override
 	{
-		if (!bind()) {
+		DeviceScope scope(this);
+		if (!scope.ok) {
 			return false;
 		}
 		if (rows <= 0 || row_len <= 0) {
@@ -401,7 +461,8 @@ public:
 
 	bool sync(void* stream) override
 	{
-		return bind() && check(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)), "cudaStreamSynchronize");
+		DeviceScope scope(this);
+		return scope.ok && check(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)), "cudaStreamSynchronize");
 	}
 
 	void* stream_create() override
@@ -422,7 +483,8 @@ public:
 
 	bool stream_wait(void* waiter, void* signal) override
 	{
-		if (!bind()) {
+		DeviceScope scope(this);
+		if (!scope.ok) {
 			return false;
 		}
 		if (events_.empty()) {
@@ -439,6 +501,7 @@ public:
 	~CudaBackend() override
 	{
 		cudaFree(bus_partial_);
+		cudaFree(zero_tiles_);
 		for (cudaEvent_t ev : events_) {
 			if (ev) {
 				cudaEventDestroy(ev);
@@ -453,6 +516,8 @@ private:
 	std::string error_;
 	std::vector<cudaEvent_t> events_;
 	size_t next_event_ = 0;
+	void* zero_tiles_ = nullptr;       // device copy of zero_lanes' tile list
+	size_t zero_tiles_bytes_ = 0;
 	void* bus_partial_ = nullptr;      // row-group partial sums of the bus reduction
 	size_t bus_partial_bytes_ = 0;
 };

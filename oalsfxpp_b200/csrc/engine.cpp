@@ -145,6 +145,43 @@ struct oalsfx_engine {
 	bool groups_dirty = true;
 	long long launches = 0;
 	int last_kernel = -1;               // id of the most recent mix kernel launched (oalsfx_engine_last_kernel)
+	// Host buffers the engine has page-locked in place (oalsfx_engine_pin_host, or on first sight with OALSFX_PIN_HOST=1)
+	struct PinnedHost { void* p; size_t bytes; bool automatic; };
+	std::vector<PinnedHost> pinned_host;
+	bool auto_pin_host = false;
+	bool pin_host(void* p, size_t bytes, bool automatic)
+	{
+		for (PinnedHost& h : pinned_host) {
+			if (h.p == p && h.bytes >= bytes) {
+				return true;
+			}
+		}
+		// a new size or place: automatic registrations that overlap it are stale (the caller's buffer moved)
+		for (size_t i = 0; i < pinned_host.size();) {
+			const char* a0 = static_cast<const char*>(pinned_host[i].p);
+			const char* b0 = static_cast<const char*>(p);
+			if (pinned_host[i].automatic && a0 < b0 + bytes && b0 < a0 + pinned_host[i].bytes) {
+				be->host_unregister(pinned_host[i].p);
+				pinned_host.erase(pinned_host.begin() + static_cast<long>(i));
+			} else {
+				++i;
+			}
+		}
+		if (automatic && pinned_host.size() >= 16) { // keep the table small: forget the oldest automatic entry
+			for (size_t i = 0; i < pinned_host.size(); ++i) {
+				if (pinned_host[i].automatic) {
+					be->host_unregister(pinned_host[i].p);
+					pinned_host.erase(pinned_host.begin() + static_cast<long>(i));
+					break;
+				}
+			}
+		}
+		if (!be->host_register(p, bytes)) {
+			return false;
+		}
+		pinned_host.push_back(PinnedHost{p, bytes, automatic});
+		return true;
+	}
 
 	bool mix_launch(int id, const MixArgs& a, void* stream)
 	{
@@ -186,6 +223,9 @@ struct oalsfx_engine {
 		be->release(lane_send_dev);
 		for (int s = 0; s < kMaxSlots; ++s) {
 			be->release(lane_class_dev[s]);
+		}
+		for (const PinnedHost& h : pinned_host) {
+			be->host_unregister(h.p);
 		}
 		be->release(stage_in);
 		be->release(stage_out);
@@ -1024,6 +1064,9 @@ int oalsfx_engine_create(const oalsfx_engine_desc* desc, oalsfx_engine** out)
 	if (const char* fam = std::getenv("OALSFX_KERNEL")) {
 		e->family = (std::strcmp(fam, "single") == 0 ? 0 : std::strcmp(fam, "quartet") == 0 ? 3 : std::strcmp(fam, "duo") == 0 ? 4 : std::strcmp(fam, "relay") == 0 ? 5 : std::strcmp(fam, "span") == 0 ? 6 : 2);
 	}
+	if (const char* ph = std::getenv("OALSFX_PIN_HOST")) {
+		e->auto_pin_host = std::atoi(ph) != 0;
+	}
 	if (const char* sb = std::getenv("OALSFX_SPAN_BULK")) {
 		e->family_span_bulk = std::atoi(sb);
 	}
@@ -1176,6 +1219,12 @@ int oalsfx_engine_mix(oalsfx_engine* e, int frames, const float* src, float* dst
 	const float* dsrc = src;
 	float* ddst = dst;
 	e->note_stream(cuda_stream);
+	if (space == OALSFX_SPACE_HOST && e->auto_pin_host) {
+		// pageable buffers copy at a fraction of the pinned rate and do not overlap with the kernels: lock them in place
+		// (a failure only means the copies stay slow)
+		e->pin_host(const_cast<float*>(src), count * sizeof(float), true);
+		e->pin_host(dst, count * sizeof(float), true);
+	}
 	if (space == OALSFX_SPACE_HOST) {
 		if (count > e->stage_cap) {
 			e->be->sync(cuda_stream);
@@ -1282,6 +1331,30 @@ int oalsfx_engine_mix(oalsfx_engine* e, int frames, const float* src, float* dst
 		}
 	}
 	return OALSFX_OK;
+}
+
+int oalsfx_engine_pin_host(oalsfx_engine* e, void* buffer, size_t bytes)
+{
+	if (!e || !buffer || bytes == 0) {
+		return e ? e->fail(OALSFX_ERR_ARGUMENT, "Bad pin_host arguments.") : OALSFX_ERR_ARGUMENT;
+	}
+	return e->pin_host(buffer, bytes, false) ? OALSFX_OK : e->fail(OALSFX_ERR_DEVICE, "Page-locking the buffer failed: " + e->be->error());
+}
+
+int oalsfx_engine_unpin_host(oalsfx_engine* e, void* buffer)
+{
+	if (!e || !buffer) {
+		return e ? e->fail(OALSFX_ERR_ARGUMENT, "Bad unpin_host arguments.") : OALSFX_ERR_ARGUMENT;
+	}
+	e->quiesce();
+	for (size_t i = 0; i < e->pinned_host.size(); ++i) {
+		if (e->pinned_host[i].p == buffer) {
+			e->be->host_unregister(buffer);
+			e->pinned_host.erase(e->pinned_host.begin() + static_cast<long>(i));
+			return OALSFX_OK;
+		}
+	}
+	return e->fail(OALSFX_ERR_ARGUMENT, "The buffer is not pinned by this engine.");
 }
 
 int oalsfx_engine_mix_bus(oalsfx_engine* e, int frames, const float* src, float* dst, int layout, float* bus, void* cuda_stream)

@@ -53,6 +53,10 @@ def bind(lib):
     lib.oalsfx_engine_set_sends.restype = i32
     lib.oalsfx_engine_mix.argtypes = [vp, i32, vp, vp, i32, i32, vp]
     lib.oalsfx_engine_mix.restype = i32
+    lib.oalsfx_engine_pin_host.argtypes = [vp, vp, C.c_size_t]
+    lib.oalsfx_engine_pin_host.restype = i32
+    lib.oalsfx_engine_unpin_host.argtypes = [vp, vp]
+    lib.oalsfx_engine_unpin_host.restype = i32
     lib.oalsfx_engine_mix_bus.argtypes = [vp, i32, vp, vp, i32, vp, vp]
     lib.oalsfx_engine_mix_bus.restype = i32
     lib.oalsfx_engine_reduce_bus.argtypes = [vp, i32, vp, i32, vp, vp]
@@ -93,6 +97,7 @@ def bind(lib):
 EXPORTED_SYMBOLS = (
     "oalsfx_engine_create", "oalsfx_engine_destroy", "oalsfx_engine_set_effect",
     "oalsfx_engine_set_sends", "oalsfx_engine_mix", "oalsfx_engine_mix_bus", "oalsfx_engine_reduce_bus",
+    "oalsfx_engine_pin_host", "oalsfx_engine_unpin_host",
     "oalsfx_engine_debug_state", "oalsfx_engine_launch_count", "oalsfx_engine_last_kernel", "oalsfx_engine_device_bytes",
     "oalsfx_last_error", "oalsfx_build_info", "oalsfx_effect_defaults", "oalsfx_effect_normalize",
     "oalsfx_reverb_preset", "oalsfx_reverb_preset_name", "oalsfx_pcm_to_float", "oalsfx_float_to_s16",
@@ -209,6 +214,13 @@ class Engine:
         self._check(self.lib.oalsfx_engine_mix(self._h, int(frames), _ptr(src), _ptr(dst), layout, space,
                                                C.c_void_p(stream)))
         return dst
+
+    def pin_host(self, array):
+        """Page-lock a numpy buffer in place (see oalsfx_engine_pin_host); keep it alive until unpin_host / close."""
+        self._check(self.lib.oalsfx_engine_pin_host(self._h, array.ctypes.data, array.nbytes))
+
+    def unpin_host(self, array):
+        self._check(self.lib.oalsfx_engine_unpin_host(self._h, array.ctypes.data))
 
     def mix_bus(self, src, dst, frames, bus, layout=LAYOUT_STREAM_MAJOR, stream=0):
         """mix() on device buffers that also fills `bus` ([frames][channels], device) with the sum of the output over all
