@@ -134,6 +134,101 @@ def test_ten_seconds_per_effect(checker, effect):
         _assert_match(expect, y[s], effect != T.ring_modulator, f"{effect.name} stream {s}")
 
 
+def _ten_seconds_at_full_size(checker, streams, fmt, rate, slots, exact, unique=32, check=(0, 5, 17, 31)):
+    """10 s of audio at a BASELINE configuration's full stream count, device buffers, block by block.  Stream s is fed
+    input s mod `unique` (the inputs are independent noise): every copy must equal the first one bit for bit after every
+    block, and the `check` inputs are compared with the checker over the whole 10 s."""
+    import torch
+    lib = _lib()
+    block, total = 1024, 10 * rate
+    blocks = H.blocks_of(total, block)
+    C = ox.channel_count(fmt)
+    base = np.stack([H.noise(9000 + k, C, total) for k in range(unique)])
+    base_dev = torch.from_numpy(base).cuda()
+    kept = {k: [] for k in check}
+    kernels = set()
+    assert streams % unique == 0
+    with ox.Engine(streams, fmt, rate, len(slots), lib=lib) as eng:
+        for i, (t, p) in enumerate(slots):
+            eng.set_effect(i, t, p)
+        pos = 0
+        for n in blocks:
+            x = base_dev[:, pos:pos + n].repeat(streams // unique, 1, 1).contiguous()
+            y = torch.empty_like(x)
+            eng.mix(x, y, frames=n, stream=torch.cuda.current_stream().cuda_stream)
+            per = y.view(streams // unique, unique, n, C)
+            assert bool((per == per[0:1]).all()), f"streams with identical input diverged in the block at frame {pos}"
+            for k in check:
+                kept[k].append(per[0, k].cpu().numpy())
+            kernels.add(eng.last_kernel)
+            pos += n
+        ints = [eng.debug_state(s, slot) for s in (0, streams - 1) for slot in range(len(slots))]
+    script = H.simple_script(slots, blocks)
+    for k in check:
+        expect = H.run_script_orc(checker, fmt, rate, len(slots), script, base[k])
+        _assert_match(expect, np.concatenate(kept[k], axis=0), exact, f"input {k}")
+    return kernels, ints
+
+
+def test_cfg1_ten_seconds_at_full_size(checker):
+    """BASELINE cfg1: EAX reverb on 1024 mono 48 kHz streams, 10 s in 1024-frame blocks (the span kernel serves every
+    block but the first), bit-exact; ring offset and cross-fade counter at the end."""
+    kernels, ints = _ten_seconds_at_full_size(checker, 1024, F.mono, 48000, [(T.eax_reverb, None)], True)
+    assert any(k.startswith("kSpan") for k in kernels), kernels
+    for st in ints:
+        assert st["offset"] == 480000 and st["fade_count"] == 128
+
+
+def test_cfg3_ten_seconds_at_full_size(checker):
+    """BASELINE cfg3: flanger (sinusoid LFO: its whole period of 355 556 samples is visited 2.7 times) + ring modulator +
+    distortion + compressor on 16 384 mono streams at 96 kHz, 10 s; within 1e-5 (the ring modulator's carrier is the one
+    device sinf), integer state exact."""
+    lib = _lib()
+    rate = 96000
+    slots = [(T.flanger, ox.default_props(T.flanger, lib=lib, waveform_=0)), (T.ring_modulator, None), (T.distortion, None), (T.compressor, None)]
+    kernels, ints = _ten_seconds_at_full_size(checker, 16384, F.mono, rate, slots, False, check=(0, 13, 31))
+    total = 10 * rate
+    step = int(np.float32(440.0) * np.float32(1 << 24) / np.float32(rate))
+    for i, st in enumerate(ints):
+        slot = i % 4
+        if slot == 0:
+            assert st["offset"] == total, st                         # flanger ring offset (oalsfxpp.cpp:5484)
+        elif slot == 1:
+            assert st["ring_mod_index"] == (total * step) & 0xFFFFFF, st   # oalsfxpp.cpp:5722-5738
+
+
+@pytest.mark.parametrize("family", ["single", "duo", "quartet", "relay", "span"])
+def test_integer_state_agrees_across_kernel_families(family, monkeypatch):
+    """Ring offsets, the reverb's cross-fade counter and modulator index, the chorus offset: after every block, whichever
+    kernel family ran it, they follow the reference's formulas (offset_ += n, oalsfxpp.cpp:7853 / 4212 / 4962; fade 128
+    samples from an update that changes a tap, :6118-6138; modulator index modulo its range, :7443-7470)."""
+    monkeypatch.setenv("OALSFX_KERNEL", family)
+    lib = _lib()
+    rate, S = 48000, 96
+    mod_time = 0.25
+    chain = [T.equalizer, T.chorus, T.echo, T.eax_reverb]
+    blocks = [1024, 100, 2048, 77, 1024, 1024, 6]
+    change_at = 4
+    with ox.Engine(S, F.stereo, rate, 4, lib=lib) as eng:
+        for i, t in enumerate(chain):
+            eng.set_effect(i, t)
+        eng.set_effect(3, T.eax_reverb, ox.default_props(T.eax_reverb, lib=lib, modulation_depth_=0.3, modulation_time_=mod_time))
+        total, since = 0, 0
+        for b, n in enumerate(blocks):
+            if b == change_at:  # a tap change: the cross-fade counter restarts
+                eng.set_effect(3, T.eax_reverb, ox.default_props(T.eax_reverb, lib=lib, modulation_depth_=0.3, modulation_time_=mod_time,
+                                                               reflections_delay_=0.02))
+                since = 0
+            eng.mix(np.zeros((S, n, 2), np.float32))
+            total += n
+            since += n
+            for s in (0, 31, 32, S - 1):
+                st = eng.debug_state(s, 3)
+                assert st["offset"] == total and st["fade_count"] == min(since, 128), (family, b, s, st)
+                assert st["mod_index"] == total % int(mod_time * rate), (family, b, s, st)
+                assert eng.debug_state(s, 1)["offset"] == total and eng.debug_state(s, 2)["offset"] == total
+
+
 def test_cfg2_schedule_on_4096_streams(checker):
     """BASELINE cfg2: 4-slot chain, 4096 stereo streams, per-block parameter changes (reverb gain ramp,
     tap cross-fade every 16th block, EQ step); a sample of streams compared with the checker."""
