@@ -872,25 +872,28 @@ struct oalsfx_engine {
 		}
 		const SendClass& sc = send_classes[static_cast<size_t>(g.key.send)];
 		int kinds[kMaxSlots];
-		bool any_filter = sc.direct_coef.filter_type != 0;
+		bool send_filter = sc.direct_coef.filter_type != 0;   // a send's shelf filter is active (apply_filters, oalsfxpp.cpp:3101-3143)
+		bool unstable = false;
 		for (int s = 0; s < kMaxSlots; ++s) {
 			const int type = classes[static_cast<size_t>(g.key.fx[s])].type;
 			kinds[s] = kind_of_type(type);
 			if (kinds[s] != kKindNull && sc.aux_coef[s].filter_type != 0) {
-				any_filter = true;
+				send_filter = true;
 			}
 			if (classes[static_cast<size_t>(g.key.fx[s])].coef.flags & kCoefUnstable) {
-				any_filter = true; // keeps the group on the exact (generic) kernels, see coefs.h
+				unstable = true; // keeps the group on the exact (generic) kernels, see coefs.h
 			}
 		}
+		const bool any_filter = send_filter || unstable;
 		// The relay pipeline (relay.cuh): any signature of two or more effects in one launch, one warp per effect.
 		const bool whole_tiles_group = g.identity || g.full_tiles;
 		int active = 0;
 		for (int s = 0; s < kMaxSlots; ++s) {
 			active += kinds[s] != kKindNull ? 1 : 0;
 		}
-		const bool relay_ok = be->has_relay() && !any_filter && frames >= 2 && whole_tiles_group &&
-			(channels == 1 || channels == 2) && active >= 2 && family != 0;
+		// (with an active send filter the relay's filter-carrying variant is the only one-launch kernel: also for one slot)
+		const bool relay_ok = be->has_relay() && !unstable && frames >= 2 && whole_tiles_group &&
+			(channels == 1 || channels == 2) && active >= (send_filter ? 1 : 2) && family != 0;
 		auto launch_relay = [&]() {
 			MixArgs a;
 			fill_common(a, g, frames, src, dst, layout, frames_total, frame0);
@@ -912,6 +915,9 @@ struct oalsfx_engine {
 			a.relay_smem_floats = floats;
 			sanitize_gains(a);
 			++launches;
+			if (send_filter) {
+				return mix_launch(channels == 1 ? (heavy ? kRelaySfMonoHeavy : kRelaySfMono) : (heavy ? kRelaySfStereoHeavy : kRelaySfStereo), a, stream);
+			}
 			return mix_launch(channels == 1 ? (heavy ? kRelayMonoHeavy : kRelayMono) : (heavy ? kRelayStereoHeavy : kRelayStereo), a, stream);
 		};
 		if (relay_ok && family == 5) { // OALSFX_KERNEL=relay: wherever eligible (A/B measurements, parity tests)

@@ -36,6 +36,13 @@ bool launch_relay_family(int kernel_id, const MixArgs& args, cudaStream_t st)
 		return true;
 		OALSFX_RELAY_MULTI_TABLE(OALSFX_RX)
 #undef OALSFX_RX
+#define OALSFX_RX(id, CT, HEAVY) \
+	case id: \
+		relay_attributes(done[id], relay::relay_sf_kernel<CT, HEAVY>); \
+		relay::relay_sf_kernel<CT, HEAVY><<<static_cast<unsigned>(args.tile_count), relay::kThreads, dyn, st>>>(args); \
+		return true;
+		OALSFX_RELAY_SF_TABLE(OALSFX_RX)
+#undef OALSFX_RX
 	default: return false;
 	}
 }

@@ -70,6 +70,12 @@
 	RX(kRelayStereo, 2, false) \
 	RX(kRelayMonoHeavy, 1, true) \
 	RX(kRelayStereoHeavy, 2, true)
+// the same with the sends' shelf filters compiled in (relay_sf_kernel)
+#define OALSFX_RELAY_SF_TABLE(RX) \
+	RX(kRelaySfMono, 1, false) \
+	RX(kRelaySfStereo, 2, false) \
+	RX(kRelaySfMonoHeavy, 1, true) \
+	RX(kRelaySfStereoHeavy, 2, true)
 // the same with one parameter class per tile (relay_multi_kernel)
 #define OALSFX_RELAY_MULTI_TABLE(RX) \
 	RX(kRelayMultiMono, 1, false) \
@@ -117,6 +123,7 @@ enum KernelId : int {
 #define OALSFX_RX(id, CT, HEAVY) id,
 	OALSFX_RELAY_TABLE(OALSFX_RX)
 	OALSFX_RELAY_MULTI_TABLE(OALSFX_RX)
+	OALSFX_RELAY_SF_TABLE(OALSFX_RX)
 #undef OALSFX_RX
 #define OALSFX_SX(id, CT, SL, CHAIN) id,
 	OALSFX_SPAN_TABLE(OALSFX_SX)
@@ -231,6 +238,7 @@ inline const char* kernel_name(int id)
 #define OALSFX_RX(rid, CT, HEAVY) if (id == rid) return #rid;
 	OALSFX_RELAY_TABLE(OALSFX_RX)
 	OALSFX_RELAY_MULTI_TABLE(OALSFX_RX)
+	OALSFX_RELAY_SF_TABLE(OALSFX_RX)
 #undef OALSFX_RX
 #define OALSFX_SX(sid, CT, SL, CHAIN) if (id == sid) return #sid;
 	OALSFX_SPAN_TABLE(OALSFX_SX)

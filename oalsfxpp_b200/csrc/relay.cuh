@@ -46,7 +46,10 @@ struct Shared {
 	float win_in[kFwSlots][CT][kLanes];              // stage 0: input frames in flight
 };
 
-template <int CT, int P, class Fx>
+// SF: the sends' shelf filters are compiled in (apply_filters, oalsfxpp.cpp:3101-3143): every stage filters the input
+// frame with ITS aux send's filters before the wet encode, stage 0 the direct send's as well, and the filter histories
+// are state (oalsfxpp.cpp:1097-1113) instead of "the last two input samples".
+template <int CT, int P, class Fx, bool SF = false>
 __device__ __forceinline__ void stage(const MixArgs& a, Shared<CT>& sh, float* dyn, const int tile, const int lane)
 {
 	constexpr bool kReverb = std::is_same<Fx, FxReverb>::value;
@@ -63,8 +66,15 @@ __device__ __forceinline__ void stage(const MixArgs& a, Shared<CT>& sh, float* d
 	const bool fast_out = a.io_cs == 1 && a.io_fs == CT && (a.frames % kChunk) == 0 && (a.io_ls % 4) == 0 &&
 		(a.io_ts % 4) == 0 && (reinterpret_cast<unsigned long long>(a.dst) & 15ULL) == 0;
 
-	SlotRunner<CT, false, Fx> r;
+	SlotRunner<CT, SF, Fx> r;
 	float* win = dyn + a.relay_win[P];
+	SendHist dhist[SF ? CT : 1];   // stage 0: the direct send's filter histories
+	if (SF && P == 0) {
+#pragma unroll
+		for (int c = 0; c < CT; ++c) {
+			load_words(dhist[c], ss + c * 8 * kLanes);
+		}
+	}
 	r.begin(a, P, tile, lane, (kReverb || kMod) ? win + lane : kEcho ? win + lane + 2 * kLanes : nullptr);
 
 	// Stage 0 input.  Through the cp.async window, kFwDepth frames ahead, in the same commit groups as the
@@ -147,7 +157,7 @@ __device__ __forceinline__ void stage(const MixArgs& a, Shared<CT>& sh, float* d
 				// direct send (oalsfxpp.cpp:2924-2950); gains sanitized by the host
 #pragma unroll
 				for (int c = 0; c < CT; ++c) {
-					pan_add<CT, true>(acc, CT, a.direct.gains[c], x[c]);
+					pan_add<CT, true>(acc, CT, a.direct.gains[c], SF ? send_filter_step(a.direct, dhist[SF ? c : 0], x[c]) : x[c]);
 				}
 			} else {
 #pragma unroll
@@ -196,6 +206,16 @@ __device__ __forceinline__ void stage(const MixArgs& a, Shared<CT>& sh, float* d
 	if (!kReverb) {
 		cp_async_wait_group<0>();
 	}
+	if (SF) {
+		r.end(a, P, tile, lane, nullptr, nullptr);   // effect state + this send's filter histories
+		if (P == 0) {
+#pragma unroll
+			for (int c = 0; c < CT; ++c) {
+				store_words(dhist[c], ss + c * 8 * kLanes);
+			}
+		}
+		return;
+	}
 	r.end_state_only(a, P, tile, lane);
 	if (P == 0) {
 		duo::store_passthrough_history<CT>(ss, 0, src, a, io_ok);
@@ -203,27 +223,27 @@ __device__ __forceinline__ void stage(const MixArgs& a, Shared<CT>& sh, float* d
 	duo::store_passthrough_history<CT>(ss, 1 + a.aux_index[P], src, a, io_ok);
 }
 
-template <int CT, bool HEAVY, int P>
+template <int CT, bool HEAVY, int P, bool SF>
 __device__ __forceinline__ void dispatch(const MixArgs& a, Shared<CT>& sh, float* dyn, int tile, int lane)
 {
 	switch (a.relay_kind[P]) {
-	case kKindModDelay: stage<CT, P, FxModDelay>(a, sh, dyn, tile, lane); break;
-	case kKindCompressor: stage<CT, P, FxCompressor>(a, sh, dyn, tile, lane); break;
-	case kKindDedicated: stage<CT, P, FxDedicated>(a, sh, dyn, tile, lane); break;
-	case kKindDistortion: stage<CT, P, FxDistortion>(a, sh, dyn, tile, lane); break;
-	case kKindEcho: stage<CT, P, FxEcho>(a, sh, dyn, tile, lane); break;
-	case kKindEqualizer: stage<CT, P, FxEqualizer>(a, sh, dyn, tile, lane); break;
-	case kKindRingMod: stage<CT, P, FxRingMod>(a, sh, dyn, tile, lane); break;
+	case kKindModDelay: stage<CT, P, FxModDelay, SF>(a, sh, dyn, tile, lane); break;
+	case kKindCompressor: stage<CT, P, FxCompressor, SF>(a, sh, dyn, tile, lane); break;
+	case kKindDedicated: stage<CT, P, FxDedicated, SF>(a, sh, dyn, tile, lane); break;
+	case kKindDistortion: stage<CT, P, FxDistortion, SF>(a, sh, dyn, tile, lane); break;
+	case kKindEcho: stage<CT, P, FxEcho, SF>(a, sh, dyn, tile, lane); break;
+	case kKindEqualizer: stage<CT, P, FxEqualizer, SF>(a, sh, dyn, tile, lane); break;
+	case kKindRingMod: stage<CT, P, FxRingMod, SF>(a, sh, dyn, tile, lane); break;
 	case kKindReverb:
 		if (HEAVY) {
-			stage<CT, P, typename std::conditional<HEAVY, FxReverb, FxDedicated>::type>(a, sh, dyn, tile, lane);
+			stage<CT, P, typename std::conditional<HEAVY, FxReverb, FxDedicated>::type, SF>(a, sh, dyn, tile, lane);
 		}
 		break;
 	default: break;
 	}
 }
 
-template <int CT, bool HEAVY>
+template <int CT, bool HEAVY, bool SF = false>
 __device__ __forceinline__ void relay_body(const MixArgs& a)
 {
 	extern __shared__ __align__(16) float dyn[];
@@ -236,10 +256,10 @@ __device__ __forceinline__ void relay_body(const MixArgs& a)
 		return;
 	}
 	switch (st) {
-	case 0: dispatch<CT, HEAVY, 0>(a, sh, dyn, tile, lane); break;
-	case 1: dispatch<CT, HEAVY, 1>(a, sh, dyn, tile, lane); break;
-	case 2: dispatch<CT, HEAVY, 2>(a, sh, dyn, tile, lane); break;
-	default: dispatch<CT, HEAVY, 3>(a, sh, dyn, tile, lane); break;
+	case 0: dispatch<CT, HEAVY, 0, SF>(a, sh, dyn, tile, lane); break;
+	case 1: dispatch<CT, HEAVY, 1, SF>(a, sh, dyn, tile, lane); break;
+	case 2: dispatch<CT, HEAVY, 2, SF>(a, sh, dyn, tile, lane); break;
+	default: dispatch<CT, HEAVY, 3, SF>(a, sh, dyn, tile, lane); break;
 	}
 }
 
@@ -247,6 +267,13 @@ template <int CT, bool HEAVY>
 __global__ void __launch_bounds__(kThreads, HEAVY ? 2 : 4) relay_kernel(const __grid_constant__ MixArgs a)
 {
 	relay_body<CT, HEAVY>(a);
+}
+
+// The same with the sends' shelf filters compiled in.
+template <int CT, bool HEAVY>
+__global__ void __launch_bounds__(kThreads, HEAVY ? 2 : 4) relay_sf_kernel(const __grid_constant__ MixArgs a)
+{
+	relay_body<CT, HEAVY, true>(a);
 }
 
 // One parameter class PER TILE (as duo_multi_kernel, duo.cuh): the tile's coefficient blocks and pending bits come

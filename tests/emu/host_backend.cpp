@@ -90,6 +90,7 @@ public:
 		bool is_relay = false;
 #define OALSFX_RX(id, CT, HEAVY) is_relay = is_relay || kernel_id == id;
 		OALSFX_RELAY_TABLE(OALSFX_RX)
+		OALSFX_RELAY_SF_TABLE(OALSFX_RX)
 #undef OALSFX_RX
 		if (is_relay) {
 			static const int gen_for_kind[] = {kGenDry, kGenModDelay, kGenCompressor, kGenDedicated, kGenDistortion,

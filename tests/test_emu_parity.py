@@ -235,3 +235,8 @@ def test_mix_bus_host_logic():
         assert np.array_equal(y.view(np.uint32), y2.view(np.uint32))
         want = y.astype(np.float64).sum(axis=0)
         assert np.max(np.abs(bus - want)) <= 1e-5 * np.sqrt(streams)
+
+
+@pytest.mark.parametrize("case", ["chain-stereo", "echo-mono"])
+def test_send_filter_relay_selection(checker, case, monkeypatch):
+    _gpu_scenarios(monkeypatch).test_send_shelf_filters_run_in_one_launch(checker, case)

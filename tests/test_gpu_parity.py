@@ -554,6 +554,48 @@ def test_span_kernel_every_tile_share(checker, tiles):
         _assert_match(expect, per[0, k].cpu().numpy(), True, f"span share, {tiles} tiles, input {k}")
 
 
+@pytest.mark.parametrize("case", ["chain-stereo", "echo-mono", "reverb-eq-stereo"])
+def test_send_shelf_filters_run_in_one_launch(checker, case):
+    """Active send shelf filters (apply_filters, oalsfxpp.cpp:3101-3143) used to drop a group to one exact pass per slot;
+    the relay pipeline now carries them (relay_sf_kernel: every stage filters the input with its own send's filters, the
+    histories are state): one launch per block, bit-exact, also when the send settings change between blocks."""
+    lib = _lib()
+    fmt = F.mono if case == "echo-mono" else F.stereo
+    slots = {"chain-stereo": [T.equalizer, T.chorus, T.echo, T.eax_reverb], "echo-mono": [T.echo],
+             "reverb-eq-stereo": [T.eax_reverb, T.null, T.equalizer]}[case]
+    sends_a = {-1: (0.8, 0.5, 1.0), 0: (0.7, 1.0, 0.4), 2: (1.0, 0.25, 0.5)}
+    sends_b = {-1: (1.0, 1.0, 0.3), 0: (0.9, 0.3, 0.6)}
+    S, blocks = 70, [1024, 333, 1024, 2, 640]
+    C = ox.channel_count(fmt)
+    total = sum(blocks)
+    x = np.stack([H.noise(5000 + s, C, total) for s in range(S)])
+    y = np.empty_like(x)
+    script = [("type", i, t) for i, t in enumerate(slots)]
+
+    def apply_sends(eng, sends):
+        triples = [sends.get(i, (1.0, 1.0, 1.0)) for i in range(len(slots))]
+        eng.set_sends(direct=sends.get(-1, (1.0, 1.0, 1.0)), aux=triples)
+        return [("send", i, sends.get(i, (1.0, 1.0, 1.0))) for i in range(-1, len(slots))] + [("apply",)]
+
+    with ox.Engine(S, fmt, 48000, len(slots), lib=lib) as eng:
+        for i, t in enumerate(slots):
+            eng.set_effect(i, t)
+        script += apply_sends(eng, sends_a)
+        at = 0
+        for b, n in enumerate(blocks):
+            if b == 3:
+                script += apply_sends(eng, sends_b)
+            before = eng.launch_count
+            y[:, at:at + n] = eng.mix(np.ascontiguousarray(x[:, at:at + n]))
+            assert eng.launch_count - before == 1, (case, b, eng.last_kernel)
+            assert eng.last_kernel.startswith("kRelaySf"), eng.last_kernel
+            script += [("mix", n)]
+            at += n
+    for s in (0, 31, 32, 64, S - 1):
+        expect = H.run_script_orc(checker, fmt, 48000, len(slots), script, x[s])
+        _assert_match(expect, y[s], True, f"{case} stream {s}")
+
+
 RELAY_SIGNATURES = [
     # (format, rate, slots) -- none of these has a fused kernel of its own: the relay pipeline runs them in one launch
     (F.stereo, 48000, [T.echo, T.eax_reverb]),
