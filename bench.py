@@ -402,9 +402,17 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     bus_ms = float(t.item())
+    # the reduction pass alone (events around it; the subtraction above is between two timed regions and noisy)
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for _ in range(bus_steps):
+        eng.reduce_bus(F, y, bus, stream=stream)
+    r1.record()
+    torch.cuda.synchronize()
+    reduce_ms = r0.elapsed_time(r1) / bus_steps
     bus_check = float((bus.double() - (y.double().sum(dim=0) if world == 1 else bus.double())).abs().max().item())
     bus_info = {"ms_per_block_mix_plus_bus": bus_ms, "extra_ms_per_block": bus_ms - total_ms_max / args.steps,
-                "kernel": bus_kernel,
+                "reduce_pass_ms_per_block": reduce_ms, "kernel": bus_kernel,
                 "what": "oalsfx_engine_mix_bus: mix + oalsfx_engine_reduce_bus (two coalesced passes over the block's output) on one stream" +
                         (f" + NCCL all_reduce of [{F}][{C}] fp32 over {world} GPUs" if world > 1 else ""),
                 "bytes_read_for_the_bus_per_gpu": S * F * C * 4,

@@ -368,7 +368,7 @@ public:
 		}
 		cudaStream_t st = static_cast<cudaStream_t>(stream);
 		if (!(launch_duo_family(kernel_id, args, st) || launch_span_family(kernel_id, args, st) || launch_quartet_family(kernel_id, args, st) ||
-				launch_relay_family(kernel_id, args, st) || launch_mix_family(kernel_id, args, st))) {
+				launch_relay_family(kernel_id, args, st) || launch_scan_family(kernel_id, args, st) || launch_mix_family(kernel_id, args, st))) {
 			error_ = "unknown kernel id";
 			return false;
 		}

@@ -195,6 +195,7 @@ struct oalsfx_engine {
 	// 6 = as automatic (names the span kernel's tests).  OALSFX_KERNEL=auto|quartet|duo|single|relay|span overrides
 	// (A/B measurements and the parity tests of every family).
 	int family = 2;
+	bool scan_enabled = false;          // OALSFX_SCAN=1
 	int family_span_bulk = 1;           // OALSFX_SPAN_BULK=0: whole-tile spans stay on the load / store kernel; 2: whole tiles (and the bulk kernel) however few (A/B, tests)
 	// Host-buffer mix: tile slice the next launches are restricted to (0 = all tiles), and the
 	// engine-owned streams that overlap H2D, kernels and D2H of consecutive slices.
@@ -923,6 +924,22 @@ struct oalsfx_engine {
 		if (relay_ok && family == 5) { // OALSFX_KERNEL=relay: wherever eligible (A/B measurements, parity tests)
 			return launch_relay();
 		}
+		// Opt-in (OALSFX_SCAN=1): a lone equalizer slot on few streams as a linear-recurrence scan over time (scan.cuh).
+		// Re-associates the filter sums: within 1e-5 of the reference, not bit-exact -- hence never chosen by default.
+		if (scan_enabled && be->has_relay() && active == 1 && !any_filter && g.identity && slice_count == 0 &&
+			(channels == 1 || channels == 2) && frames >= 64 && streams <= 4096) {
+			for (int s = 0; s < kMaxSlots; ++s) {
+				if (kinds[s] == kKindEqualizer) {
+					MixArgs a;
+					fill_common(a, g, frames, src, dst, layout, frames_total, frame0);
+					a.with_dry = 1;
+					fill_slot(a, g, 0, s, first_block);
+					sanitize_gains(a);
+					++launches;
+					return mix_launch(channels == 1 ? kScanEqualizerMono : kScanEqualizerStereo, a, stream);
+				}
+			}
+		}
 		// A fused single-pass kernel for this signature?
 		const KernelInfo* infos = kernel_infos();
 		for (int k = 0; k < kKernelCount; ++k) {
@@ -1069,6 +1086,9 @@ int oalsfx_engine_create(const oalsfx_engine_desc* desc, oalsfx_engine** out)
 	e->slots = desc->effect_count;
 	if (const char* fam = std::getenv("OALSFX_KERNEL")) {
 		e->family = (std::strcmp(fam, "single") == 0 ? 0 : std::strcmp(fam, "quartet") == 0 ? 3 : std::strcmp(fam, "duo") == 0 ? 4 : std::strcmp(fam, "relay") == 0 ? 5 : std::strcmp(fam, "span") == 0 ? 6 : 2);
+	}
+	if (const char* sc = std::getenv("OALSFX_SCAN")) {
+		e->scan_enabled = std::atoi(sc) != 0;
 	}
 	if (const char* ph = std::getenv("OALSFX_PIN_HOST")) {
 		e->auto_pin_host = std::atoi(ph) != 0;

@@ -103,6 +103,12 @@
 	BX(kSpanBulkReverbStereo, 2, false) \
 	BX(kSpanBulkChainStereo, 2, true)
 
+// Scan kernels (scan.cuh): a lone equalizer slot as a chunked linear-recurrence scan over time, opt-in (re-associates).
+// SCX(id, CT).
+#define OALSFX_SCAN_TABLE(SCX) \
+	SCX(kScanEqualizerMono, 1) \
+	SCX(kScanEqualizerStereo, 2)
+
 namespace oalsfx {
 
 enum KernelId : int {
@@ -134,6 +140,9 @@ enum KernelId : int {
 #define OALSFX_MX(id, CT, F0, F1, F2, F3, duo) id,
 	OALSFX_MULTI_TABLE(OALSFX_MX)
 #undef OALSFX_MX
+#define OALSFX_SCX(id, CT) id,
+	OALSFX_SCAN_TABLE(OALSFX_SCX)
+#undef OALSFX_SCX
 	kKernelEnd
 };
 
@@ -249,6 +258,9 @@ inline const char* kernel_name(int id)
 #define OALSFX_MX(mid, CT, F0, F1, F2, F3, duo) if (id == mid) return #mid;
 	OALSFX_MULTI_TABLE(OALSFX_MX)
 #undef OALSFX_MX
+#define OALSFX_SCX(cid, CT) if (id == cid) return #cid;
+	OALSFX_SCAN_TABLE(OALSFX_SCX)
+#undef OALSFX_SCX
 	return "?";
 }
 

@@ -18,6 +18,7 @@ bool launch_duo_family(int kernel_id, const MixArgs& args, cudaStream_t stream);
 bool launch_quartet_family(int kernel_id, const MixArgs& args, cudaStream_t stream);  // k_quartet.cu
 bool launch_relay_family(int kernel_id, const MixArgs& args, cudaStream_t stream);    // k_relay.cu: relay_kernel, relay_multi_kernel
 bool launch_span_family(int kernel_id, const MixArgs& args, cudaStream_t stream);     // k_span.cu: block-parallel in time
+bool launch_scan_family(int kernel_id, const MixArgs& args, cudaStream_t stream);     // k_scan.cu: linear-recurrence scan over time
 
 // Shared-memory carve-out of a kernel, set once.  Tuning knobs (experiments only): OALSFX_TUNE_CARVEOUT = percent or
 // -1 (driver default), OALSFX_TUNE_DYN_SMEM = bytes of unused dynamic shared memory per CTA (caps residency).

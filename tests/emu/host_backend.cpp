@@ -119,6 +119,10 @@ public:
 			}
 			return true;
 		}
+		// the scan kernels re-associate; the CPU build runs the exact single-effect pass in their place
+#define OALSFX_SCX(id, CT) if (kernel_id == id) { kernel_id = kGenEqualizer; }
+		OALSFX_SCAN_TABLE(OALSFX_SCX)
+#undef OALSFX_SCX
 		int span_twin = -1;
 #define OALSFX_SX(id, CT, SL, CHAIN) if (kernel_id == id) { span_twin = (CHAIN ? kChainStereo : CT == 1 ? kReverbMono : kReverbStereo); }
 		OALSFX_SPAN_TABLE(OALSFX_SX)

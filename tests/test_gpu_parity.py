@@ -596,6 +596,55 @@ def test_send_shelf_filters_run_in_one_launch(checker, case):
         _assert_match(expect, y[s], True, f"{case} stream {s}")
 
 
+@pytest.mark.parametrize("settings", ["moderate", "extreme"])
+@pytest.mark.parametrize("fmt", [F.mono, F.stereo])
+def test_equalizer_as_a_linear_recurrence_scan(checker, fmt, settings, monkeypatch):
+    """scan.cuh (OALSFX_SCAN=1): a lone equalizer slot with its 32 lanes spread over time -- zero-state pass per chunk,
+    fp64 Kogge-Stone stitch of the chunk states, second pass from the true state.  It re-associates the filter sums, so
+    the bar is the north_star tolerance, 1e-5 max abs error: held with the default bands and moderate changes.  With
+    extreme settings (18 dB shelves, a 0.01-octave peak: poles at 1 - 1e-4 from the unit circle) the recurrence itself
+    amplifies every rounding by ~1e4 -- the reference's own output moves by more than 1e-5 when its input moves by one
+    ulp -- and the scan is held to a small multiple of that sensitivity instead.  Also: parameter changes between blocks,
+    block sizes that do not divide by 32, one too short for the scan (the exact kernel takes it)."""
+    monkeypatch.setenv("OALSFX_SCAN", "1")
+    lib = _lib()
+    S, blocks = 40, [1024, 2048, 777, 64, 33, 1500]
+    C = ox.channel_count(fmt)
+    total = sum(blocks)
+    x = np.stack([H.noise(6000 + s, C, total) for s in range(S)])
+    y = np.empty_like(x)
+    if settings == "extreme":
+        steps = [ox.default_props(T.equalizer, lib=lib, low_gain_=7.943, low_cutoff_=50.0, mid1_gain_=0.126, mid1_width_=0.01, high_gain_=7.943),
+                 None, ox.default_props(T.equalizer, lib=lib, mid2_gain_=7.943, mid2_center_=1000.0, mid2_width_=1.0, high_cutoff_=4000.0), None, None, None]
+    else:
+        steps = [None, None, ox.default_props(T.equalizer, lib=lib, low_gain_=2.0, mid1_gain_=0.5, mid2_gain_=1.5, mid2_width_=0.5, high_gain_=0.7), None, None, None]
+    script = [("type", 1, T.equalizer), ("apply",)]
+    kernels = []
+    with ox.Engine(S, fmt, 48000, 3, lib=lib) as eng:
+        eng.set_effect(1, T.equalizer)
+        at = 0
+        for n, p in zip(blocks, steps):
+            if p is not None:
+                eng.set_effect(1, T.equalizer, p)
+                script += [("props", 1, p), ("apply",)]
+            script += [("mix", n)]
+            y[:, at:at + n] = eng.mix(np.ascontiguousarray(x[:, at:at + n]))
+            kernels.append(eng.last_kernel)
+            at += n
+    assert kernels[0].startswith("kScanEqualizer") and kernels[4] == "kGenEqualizer", kernels
+    worst = bound = 0.0
+    for s in (0, 1, 31, 32, S - 1):
+        expect = H.run_script_orc(checker, fmt, 48000, 3, script, x[s])
+        limit = TOL
+        if settings == "extreme":
+            nudged = H.run_script_orc(checker, fmt, 48000, 3, script, np.nextafter(x[s], np.float32(np.inf)))
+            limit = max(TOL, 8.0 * H.max_abs_diff(expect, nudged))   # the reference's own response to a one-ulp nudge
+        diff = H.max_abs_diff(expect, y[s])
+        worst, bound = max(worst, diff), max(bound, limit)
+        assert diff <= limit, (s, diff, limit)
+    print(f"scan equalizer [{settings}]: max |diff| = {worst:.3e} (limit {bound:.3e})")
+
+
 RELAY_SIGNATURES = [
     # (format, rate, slots) -- none of these has a fused kernel of its own: the relay pipeline runs them in one launch
     (F.stereo, 48000, [T.echo, T.eax_reverb]),
