@@ -9,15 +9,18 @@
 // so a warp can run one (stream, wet channel) with its 32 lanes spread over TIME: lane i owns the chunk of L = F / 32
 // consecutive frames [iL, (i+1)L) and
 //
-//   1. runs the recurrence over its chunk from the zero state (fp32, the reference's expression order): end state z_i
+//   1. runs the recurrence over its chunk from the zero state (fp64): end state z_i
 //   2. the chunks are stitched by a Kogge-Stone scan over the lanes -- five shuffle steps s_i += (A^L)^(2^k) s_(i - 2^k),
-//      A^L from L steps of the homogeneous recurrence, both in fp64 (a handful of operations per block) -- which gives
-//      every lane the true state at the start of its chunk
-//   3. runs the recurrence over its chunk again from that state: the outputs, which are the next band's inputs
+//      A^L from L steps of the homogeneous recurrence, in fp64 -- which gives every lane the true state at the start of
+//      its chunk
+//   3. runs the recurrence over its chunk again from that state, in fp32 and in the reference's expression order: the
+//      outputs, which are the next band's inputs
 //
-// i.e. two passes of L steps instead of one of F: 16x less dependent work per block.  The scan RE-ASSOCIATES the
-// additions: results differ from the reference's in the last bits (measured ~1e-7 at full scale, tests hold 1e-5, the
-// north_star tolerance), so this path is opt-in (OALSFX_SCAN=1) and the bit-exact kernels stay the default.
+// i.e. two passes of L steps instead of one of F: 16x less dependent work per block.  The scan RE-ASSOCIATES: every chunk
+// starts from a state that is the exactly rounded true state instead of the reference's own (noisy) one, so the result
+// is as close to the exact-arithmetic filter as the reference's is, and the two differ by the reference's rounding
+// noise -- ~1e-5 for the default bands (a 200 Hz shelf at 48 kHz amplifies every rounding by ~100), more with higher Q.
+// Hence opt-in (OALSFX_SCAN=1); the bit-exact kernels stay the default.
 //
 // CTA = 3 warps = one stream: wet channels 0, 1, 3 (channel 2 is dead, FxEqualizer::kDeadWet); then all 96 threads pan the
 // three cascade outputs onto the bus in the reference's order and write the block.
@@ -101,16 +104,20 @@ __global__ void __launch_bounds__(kThreads) scan_equalizer_kernel(const __grid_c
 				xm2 = h.x1;
 			}
 		}
-		// 1. zero-state response of the chunk
-		float zy0 = 0.0F, zy1 = 0.0F;
+		// 1. zero-state response of the chunk, in fp64: with poles near the unit circle the zero-state response is a large
+		//    transient that the homogeneous part (step 2) cancels again -- in fp32 that cancellation costs ten times the
+		//    reference's own rounding noise (measured on a 200 Hz shelf: 1.3e-4 against 1.1e-5 from the exact filter)
+		double zy0 = 0.0, zy1 = 0.0;
 		{
-			float x0 = xm1, x1 = xm2;
+			double x0 = xm1, x1 = xm2;
+			const double b0 = q.b0, b1 = q.b1, b2 = q.b2, a1 = q.a1, a2 = q.a2;
 #pragma unroll
 			for (int t = 0; t < kMaxChunk; ++t) {
 				if (t < n) {
-					const float y = (q.b0 * v[t]) + (q.b1 * x0) + (q.b2 * x1) - (q.a1 * zy0) - (q.a2 * zy1);
+					const double xv = v[t];
+					const double y = (b0 * xv) + (b1 * x0) + (b2 * x1) - (a1 * zy0) - (a2 * zy1);
 					x1 = x0;
-					x0 = v[t];
+					x0 = xv;
 					zy1 = zy0;
 					zy0 = y;
 				}
