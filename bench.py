@@ -511,7 +511,10 @@ def main():
                   "value": Ss * world * C * F / (ms_plain * 1e-3), "unit": UNIT,
                   "with_bus_in_timed_region": {"ms_per_step": ms_bus, "kernel": k_bus, "value": Ss * world * C * F / (ms_bus * 1e-3),
                                                "what": "mix + per-GPU bus (oalsfx_engine_mix_bus) + NCCL all_reduce of the [frames][channels] bus, all inside the timed region"},
-                  "vs_one_gpu_value": None}
+                  "one_gpu_same_streams": {"value": value / world, "unit": UNIT,
+                                           "what": "this run's weak leg: %d streams on ONE GPU (max over ranks)" % S}}
+        strong["speedup_over_one_gpu"] = strong["value"] / strong["one_gpu_same_streams"]["value"]
+        strong["speedup_over_one_gpu_with_bus"] = strong["with_bus_in_timed_region"]["value"] / strong["one_gpu_same_streams"]["value"]
 
     if rank != 0:
         if world > 1:
