@@ -135,6 +135,12 @@ int oalsfx_engine_restore(oalsfx_engine* e, const void* src, size_t bytes);
  * Unused entries are 0.  Synchronizes the device. */
 int oalsfx_engine_debug_state(oalsfx_engine* e, int stream, int slot, int32_t out[4]);
 
+/* Test hook: the three waveshapers of the distortion effect (oalsfxpp.cpp:4720-4722) applied to `count` samples in a
+ * DEVICE buffer with the given edge coefficient, through the very function the distortion stage runs (fx.cuh,
+ * FxDistortion::shape: the divisions as one batched correctly-rounded sequence instead of the `/` operator), so that a
+ * test can hold it bit for bit against IEEE division over the whole operand range.  Asynchronous on cuda_stream. */
+int oalsfx_debug_waveshaper(oalsfx_engine* e, const float* samples, float edge_coeff, float* out, long long count, void* cuda_stream);
+
 /* How many of the engine's kernels have been launched so far (bench.py's gpu_launches). */
 long long oalsfx_engine_launch_count(const oalsfx_engine* e);
 

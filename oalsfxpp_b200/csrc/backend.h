@@ -53,6 +53,9 @@ public:
 	//                  out = int16(scale * x * 32767.0f) (truncation); row_scale[row] receives the scale if non-null
 	virtual bool pcm_to_float(const void* src, int bits, float* dst, long long count, void* stream) = 0;
 	virtual bool float_to_s16(const float* src, int16_t* dst, int rows, long long row_len, float* row_scale, void* stream) = 0;
+	// Test hook: the distortion stage's three waveshapers (fx.cuh, FxDistortion::shape) on device buffers, four samples at a
+	// time as in the stage.
+	virtual bool debug_waveshaper(const float* samples, float edge_coeff, float* out, long long count, void* stream) = 0;
 	virtual bool sync(void* stream) = 0;
 	// Engine-owned streams for overlapping host copies with kernels (host-buffer mix): create /
 	// destroy, and "everything enqueued on `signal` so far happens before what `waiter` gets next".

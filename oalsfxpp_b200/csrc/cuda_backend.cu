@@ -58,6 +58,24 @@ __global__ void reduce_bus_kernel(const float* data, long long ts, long long ls,
 
 // ---- PCM formats either side of the path ---------------------------------------
 // HBM-bound element-wise kernels: 16-byte accesses, grid-stride over a multiple of the SM count.
+// FxDistortion::shape (fx.cuh) on plain arrays, four samples per call as in FxDistortion::step (test hook)
+__global__ void __launch_bounds__(256) debug_waveshaper_kernel(const float* __restrict__ samples, float edge_coeff, float* __restrict__ out, long long count)
+{
+	const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
+	for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < count; i += stride) {
+		float smp[4];
+		for (int k = 0; k < 4; ++k) {
+			smp[k] = samples[i + k < count ? i + k : count - 1];
+		}
+		FxDistortion::shape(smp, edge_coeff);
+		for (int k = 0; k < 4; ++k) {
+			if (i + k < count) {
+				out[i + k] = smp[k];
+			}
+		}
+	}
+}
+
 __global__ void __launch_bounds__(256) pcm16_to_float_kernel(const int16_t* __restrict__ src, float* __restrict__ dst, long long count, bool vector_ok)
 {
 	// reference: oalsfxpp_test.cpp:728-733  dst[i] = little(src[i]) / 32768.0F
@@ -444,6 +462,19 @@ public:
 			return false;
 		}
 		return check(cudaGetLastError(), "pcm_to_float");
+	}
+
+	bool debug_waveshaper(const float* samples, float edge_coeff, float* out, long long count, void* stream) override
+	{
+		DeviceScope scope(this);
+		if (!scope.ok) {
+			return false;
+		}
+		if (count <= 0) {
+			return true;
+		}
+		debug_waveshaper_kernel<<<1184, 256, 0, static_cast<cudaStream_t>(stream)>>>(samples, edge_coeff, out, count);
+		return check(cudaGetLastError(), "debug_waveshaper_kernel");
 	}
 
 	bool float_to_s16(const float* src, int16_t* dst, int rows, long long row_len, float* row_scale, void* stream) override

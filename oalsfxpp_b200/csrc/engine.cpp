@@ -1437,6 +1437,18 @@ int oalsfx_pcm_to_float(oalsfx_engine* e, const void* src, int bit_depth, float*
 	return OALSFX_OK;
 }
 
+int oalsfx_debug_waveshaper(oalsfx_engine* e, const float* samples, float edge_coeff, float* out, long long count, void* cuda_stream)
+{
+	if (!e || !samples || !out || count < 0) {
+		return e ? e->fail(OALSFX_ERR_ARGUMENT, "Bad debug_waveshaper arguments.") : OALSFX_ERR_ARGUMENT;
+	}
+	e->note_stream(cuda_stream);
+	if (!e->be->debug_waveshaper(samples, edge_coeff, out, count, cuda_stream)) {
+		return e->fail(OALSFX_ERR_DEVICE, e->be->error());
+	}
+	return OALSFX_OK;
+}
+
 int oalsfx_float_to_s16(oalsfx_engine* e, const float* src, int16_t* dst, int rows, long long row_len, float* row_scale,
 	void* cuda_stream)
 {

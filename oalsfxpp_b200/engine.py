@@ -83,6 +83,8 @@ def bind(lib):
     lib.oalsfx_reverb_preset_name.restype = C.c_char_p
     lib.oalsfx_pcm_to_float.argtypes = [vp, vp, i32, vp, C.c_longlong, vp]
     lib.oalsfx_pcm_to_float.restype = i32
+    lib.oalsfx_debug_waveshaper.argtypes = [vp, vp, C.c_float, vp, C.c_longlong, vp]
+    lib.oalsfx_debug_waveshaper.restype = i32
     lib.oalsfx_float_to_s16.argtypes = [vp, vp, vp, i32, C.c_longlong, vp, vp]
     lib.oalsfx_float_to_s16.restype = i32
     lib.oalsfx_engine_snapshot_size.argtypes = [vp]
@@ -98,7 +100,7 @@ EXPORTED_SYMBOLS = (
     "oalsfx_engine_create", "oalsfx_engine_destroy", "oalsfx_engine_set_effect",
     "oalsfx_engine_set_sends", "oalsfx_engine_mix", "oalsfx_engine_mix_bus", "oalsfx_engine_reduce_bus",
     "oalsfx_engine_pin_host", "oalsfx_engine_unpin_host",
-    "oalsfx_engine_debug_state", "oalsfx_engine_launch_count", "oalsfx_engine_last_kernel", "oalsfx_engine_device_bytes",
+    "oalsfx_engine_debug_state", "oalsfx_debug_waveshaper", "oalsfx_engine_launch_count", "oalsfx_engine_last_kernel", "oalsfx_engine_device_bytes",
     "oalsfx_last_error", "oalsfx_build_info", "oalsfx_effect_defaults", "oalsfx_effect_normalize",
     "oalsfx_reverb_preset", "oalsfx_reverb_preset_name", "oalsfx_pcm_to_float", "oalsfx_float_to_s16",
     "oalsfx_engine_snapshot_size", "oalsfx_engine_snapshot", "oalsfx_engine_restore",
@@ -238,6 +240,10 @@ class Engine:
         out = (C.c_int32 * 4)()
         self._check(self.lib.oalsfx_engine_debug_state(self._h, stream, slot, out))
         return {"offset": out[0], "fade_count": out[1], "mod_index": out[2], "ring_mod_index": out[3]}
+
+    def debug_waveshaper(self, samples, edge_coeff, out, count, stream=0):
+        """The distortion stage's three waveshapers on a device buffer (test hook)."""
+        self._check(self.lib.oalsfx_debug_waveshaper(self._h, _ptr(samples), float(edge_coeff), _ptr(out), int(count), stream))
 
     def pcm_to_float(self, src, bit_depth, dst, count, stream=0):
         """8/16-bit PCM -> float on device buffers (the reference demo's ingest, oalsfxpp_test.cpp:703-740)."""

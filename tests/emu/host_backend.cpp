@@ -246,6 +246,20 @@ public:
 		}
 		return true;
 	}
+	bool debug_waveshaper(const float* samples, float edge_coeff, float* out, long long count, void*) override
+	{
+		for (long long i = 0; i < count; i += 4) {
+			float smp[4];
+			for (int k = 0; k < 4; ++k) {
+				smp[k] = samples[i + k < count ? i + k : count - 1];
+			}
+			oalsfx::FxDistortion::shape(smp, edge_coeff);
+			for (int k = 0; k < 4 && i + k < count; ++k) {
+				out[i + k] = smp[k];
+			}
+		}
+		return true;
+	}
 	bool float_to_s16(const float* src, int16_t* dst, int rows, long long row_len, float* row_scale, void*) override
 	{
 		for (int r = 0; r < rows; ++r) {

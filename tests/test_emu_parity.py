@@ -237,6 +237,12 @@ def test_mix_bus_host_logic():
         assert np.max(np.abs(bus - want)) <= 1e-5 * np.sqrt(streams)
 
 
+def test_waveshaper_expectation(monkeypatch):
+    """The waveshaper scenario of the GPU suite on the CPU backend (the `/` operator): pins the numpy formula the GPU's
+    batched division is held against."""
+    _gpu_scenarios(monkeypatch).test_waveshaper_divisions_are_ieee_divisions()
+
+
 @pytest.mark.parametrize("case", ["chain-stereo", "echo-mono"])
 def test_send_filter_relay_selection(checker, case, monkeypatch):
     _gpu_scenarios(monkeypatch).test_send_shelf_filters_run_in_one_launch(checker, case)

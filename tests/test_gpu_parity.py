@@ -554,6 +554,50 @@ def test_span_kernel_every_tile_share(checker, tiles):
         _assert_match(expect, per[0, k].cpu().numpy(), True, f"span share, {tiles} tiles, input {k}")
 
 
+def test_waveshaper_divisions_are_ieee_divisions():
+    """The distortion stage runs its twelve divisions per sample (oalsfxpp.cpp:4720-4722) as a batched correctly-rounded
+    sequence behind one guard instead of through the `/` operator (fx.cuh, FxDistortion::shape).  Bit for bit against
+    the same formula in numpy float32 (IEEE division): samples over 80 decades of amplitude, right at the guard's edges,
+    every kind of bit pattern (zeros of both signs, denormals, infinities, NaNs), groups of four that mix fast-path and
+    slow-path samples, and edge coefficients inside and outside the guard."""
+    rng = np.random.default_rng(20)
+    n = 1 << 21
+    inputs = []
+    inputs.append((rng.standard_normal(n) * np.exp(rng.uniform(-90.0, 30.0, n))).astype(np.float32))
+    e = rng.integers(60, 142, n).astype(np.uint32)   # exponents around both ends of the guard (67 .. 134)
+    inputs.append(((rng.integers(0, 2, n).astype(np.uint32) << 31) | (e << 23) | rng.integers(0, 1 << 23, n).astype(np.uint32)).view(np.float32))
+    inputs.append(rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32).view(np.float32))
+    special = np.array([0.0, -0.0, 1e-45, -1e-45, 1e-38, 2.0 ** -61, 2.0 ** -60, -(2.0 ** -60), 1.0, -1.0, 255.99, 256.0, -256.0, 1e38,
+                        np.inf, -np.inf, np.nan], dtype=np.float32)
+    inputs.append(np.concatenate([np.repeat(special, 4), np.tile(special, 4), rng.permutation(np.repeat(special, 64))]))
+    mixed = inputs[0].copy()
+    mixed[::7] = inputs[2][: len(mixed[::7])]
+    inputs.append(mixed)
+    inputs.append(np.zeros(4096, dtype=np.float32))
+    inputs.append(-np.zeros(4096, dtype=np.float32))
+    on_device = _lib() is H.cuda_lib()   # tests/test_emu_parity.py runs this scenario on the CPU backend (host buffers)
+    with ox.Engine(32, F.mono, 48000, 1, lib=_lib()) as eng:
+        for fc in (0.0, 0.37281, 2.0, 198.0, 200.0, 200.5, 1e6, -0.5, float("inf")):
+            f = np.float32(fc)
+            for i, s in enumerate(inputs):
+                with np.errstate(all="ignore"):
+                    one = np.float32(1.0)
+                    x = ((one + f) * s / (one + (f * np.abs(s)))).astype(np.float32)
+                    x = ((one + f) * x / (one + (f * np.abs(x))) * np.float32(-1.0)).astype(np.float32)
+                    x = ((one + f) * x / (one + (f * np.abs(x)))).astype(np.float32)
+                if on_device:
+                    import torch
+                    ts = torch.from_numpy(s.copy()).to("cuda:0")
+                    out = torch.empty_like(ts)
+                    eng.debug_waveshaper(ts, fc, out, ts.numel(), stream=torch.cuda.current_stream().cuda_stream)
+                    torch.cuda.synchronize()
+                    got = out.cpu().numpy()
+                else:
+                    got = np.empty_like(s)
+                    eng.debug_waveshaper(np.ascontiguousarray(s), fc, got, s.size)
+                _assert_match(x, got, True, f"edge coefficient {fc}, input set {i}")
+
+
 @pytest.mark.parametrize("case", ["chain-stereo", "echo-mono", "reverb-eq-stereo"])
 def test_send_shelf_filters_run_in_one_launch(checker, case):
     """Active send shelf filters (apply_filters, oalsfxpp.cpp:3101-3143) used to drop a group to one exact pass per slot;
