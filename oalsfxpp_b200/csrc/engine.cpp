@@ -894,7 +894,7 @@ struct oalsfx_engine {
 		}
 		// (with an active send filter the relay's filter-carrying variant is the only one-launch kernel: also for one slot)
 		const bool relay_ok = be->has_relay() && !unstable && frames >= 2 && whole_tiles_group &&
-			(channels == 1 || channels == 2) && active >= (send_filter ? 1 : 2) && family != 0;
+			active >= (send_filter ? 1 : 2) && family != 0;
 		auto launch_relay = [&]() {
 			MixArgs a;
 			fill_common(a, g, frames, src, dst, layout, frames_total, frame0);
@@ -916,10 +916,13 @@ struct oalsfx_engine {
 			a.relay_smem_floats = floats;
 			sanitize_gains(a);
 			++launches;
+			// quad / 5.1 / 6.1 / 7.1: the kernels with a run-time channel count
 			if (send_filter) {
-				return mix_launch(channels == 1 ? (heavy ? kRelaySfMonoHeavy : kRelaySfMono) : (heavy ? kRelaySfStereoHeavy : kRelaySfStereo), a, stream);
+				return mix_launch(channels == 1 ? (heavy ? kRelaySfMonoHeavy : kRelaySfMono) : channels == 2 ? (heavy ? kRelaySfStereoHeavy : kRelaySfStereo) :
+					(heavy ? kRelaySfWideHeavy : kRelaySfWide), a, stream);
 			}
-			return mix_launch(channels == 1 ? (heavy ? kRelayMonoHeavy : kRelayMono) : (heavy ? kRelayStereoHeavy : kRelayStereo), a, stream);
+			return mix_launch(channels == 1 ? (heavy ? kRelayMonoHeavy : kRelayMono) : channels == 2 ? (heavy ? kRelayStereoHeavy : kRelayStereo) :
+				(heavy ? kRelayWideHeavy : kRelayWide), a, stream);
 		};
 		if (relay_ok && family == 5) { // OALSFX_KERNEL=relay: wherever eligible (A/B measurements, parity tests)
 			return launch_relay();

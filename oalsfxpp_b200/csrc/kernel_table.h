@@ -69,13 +69,18 @@
 	RX(kRelayMono, 1, false) \
 	RX(kRelayStereo, 2, false) \
 	RX(kRelayMonoHeavy, 1, true) \
-	RX(kRelayStereoHeavy, 2, true)
+	RX(kRelayStereoHeavy, 2, true) \
+	RX(kRelayWide, 0, false) \
+	RX(kRelayWideHeavy, 0, true)
+// (CT = 0: quad / 5.1 / 6.1 / 7.1, the channel count is a run-time value)
 // the same with the sends' shelf filters compiled in (relay_sf_kernel)
 #define OALSFX_RELAY_SF_TABLE(RX) \
 	RX(kRelaySfMono, 1, false) \
 	RX(kRelaySfStereo, 2, false) \
 	RX(kRelaySfMonoHeavy, 1, true) \
-	RX(kRelaySfStereoHeavy, 2, true)
+	RX(kRelaySfStereoHeavy, 2, true) \
+	RX(kRelaySfWide, 0, false) \
+	RX(kRelaySfWideHeavy, 0, true)
 // the same with one parameter class per tile (relay_multi_kernel)
 #define OALSFX_RELAY_MULTI_TABLE(RX) \
 	RX(kRelayMultiMono, 1, false) \

@@ -123,7 +123,7 @@ OALSFX_HD float send_filter_step(const SendCoef& sc, SendHist& h, float x)
 template <int CT, bool SF, class Fx, bool TABLE = false>
 struct SlotRunner {
 	Fx fx;
-	SendHist hist[SF ? kMaxChannels : 1];
+	SendHist hist[SF ? (CT ? CT : kMaxChannels) : 1];   // indexed by unrolled loops only: registers, not local memory
 	const SlotCoef* tab_slot = nullptr;
 	const SendCoef* tab_send = nullptr;
 
@@ -147,8 +147,11 @@ struct SlotRunner {
 		if (SF) {
 			const uint32_t* ss = a.send_state + (static_cast<long long>(tile) * kSendStateWords +
 				(1 + a.aux_index[p]) * kMaxChannels * 8) * kLanes + lane;
-			for (int c = 0; c < a.channels; ++c) {
-				load_words(hist[c], ss + c * 8 * kLanes);
+			OALSFX_UNROLL
+			for (int c = 0; c < (CT ? CT : kMaxChannels); ++c) {
+				if (CT || c < a.channels) {
+					load_words(hist[SF ? c : 0], ss + c * 8 * kLanes);
+				}
 			}
 		}
 	}
@@ -206,14 +209,17 @@ struct SlotRunner {
 		fx.template end_ct<CT>(coef(a, p), st, a.channels);
 		uint32_t* ss = a.send_state + (static_cast<long long>(tile) * kSendStateWords +
 			(1 + a.aux_index[p]) * kMaxChannels * 8) * kLanes + lane;
-		for (int c = 0; c < a.channels; ++c) {
-			if (SF) {
-				store_words(hist[c], ss + c * 8 * kLanes);
-			} else {
-				SendHist h;
-				h.lp.x0 = h.lp.y0 = h.hp.x0 = h.hp.y0 = last1[c];
-				h.lp.x1 = h.lp.y1 = h.hp.x1 = h.hp.y1 = last2[c];
-				store_words(h, ss + c * 8 * kLanes);
+		OALSFX_UNROLL
+		for (int c = 0; c < (CT ? CT : kMaxChannels); ++c) {
+			if (CT || c < a.channels) {
+				if (SF) {
+					store_words(hist[SF ? c : 0], ss + c * 8 * kLanes);
+				} else {
+					SendHist h;
+					h.lp.x0 = h.lp.y0 = h.hp.x0 = h.hp.y0 = last1[c];
+					h.lp.x1 = h.lp.y1 = h.hp.x1 = h.hp.y1 = last2[c];
+					store_words(h, ss + c * 8 * kLanes);
+				}
 			}
 		}
 	}

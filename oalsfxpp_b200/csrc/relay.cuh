@@ -40,11 +40,52 @@ namespace relay {
 constexpr int kChunk = 4;                 // frames per hand-off (= the output row batch)
 constexpr int kThreads = kMaxSlots * kLanes;
 
+// CT = 0: the device channel count is a run-time value (quad, 5.1, 6.1, 7.1: MixArgs::channels), arrays are sized for
+// kMaxChannels.
 template <int CT>
 struct Shared {
-	float xch[kMaxSlots][2][kChunk][2 * CT][kLanes]; // hand-off P -> P+1: x_0..x_C-1, bus_0..bus_C-1 (the last stage parks finished frames in its own)
-	float win_in[kFwSlots][CT][kLanes];              // stage 0: input frames in flight
+	static constexpr int NC = CT ? CT : kMaxChannels;
+	float xch[kMaxSlots][2][kChunk][2 * NC][kLanes]; // hand-off P -> P+1: x_0..x_C-1, bus_0..bus_C-1 (the last stage parks finished frames in its own)
+	float win_in[kFwSlots][NC][kLanes];              // stage 0: input frames in flight
 };
+
+// Where the exchange lives: static shared memory for one and two channels (16 / 28 KB), the head of the dynamic
+// allocation for the wide kernels (68 KB, beyond the static limit).
+template <int CT>
+struct SharedPlace {
+	static __device__ __forceinline__ Shared<CT>& get(float*&)
+	{
+		__shared__ __align__(16) Shared<CT> sh;
+		return sh;
+	}
+};
+template <>
+struct SharedPlace<0> {
+	static __device__ __forceinline__ Shared<0>& get(float*& dyn)
+	{
+		Shared<0>* sh = reinterpret_cast<Shared<0>*>(dyn);
+		dyn += sizeof(Shared<0>) / sizeof(float);
+		return *sh;
+	}
+};
+
+// No shelf filter active: a processed send's filter histories are the last two input samples (oalsfxpp.cpp:1038-1056).
+template <int CT>
+__device__ __forceinline__ void store_passthrough_history(uint32_t* ss, int send, const float* src, const MixArgs& a, bool io_ok)
+{
+	if (CT) {
+		duo::store_passthrough_history<CT ? CT : 1>(ss, send, src, a, io_ok);
+		return;
+	}
+	for (int c = 0; c < a.channels; ++c) {
+		const float last1 = io_ok ? src[(a.frames - 1) * a.io_fs + c * a.io_cs] : 0.0F;
+		const float last2 = io_ok ? src[(a.frames - 2) * a.io_fs + c * a.io_cs] : 0.0F;
+		SendHist h;
+		h.lp.x0 = h.lp.y0 = h.hp.x0 = h.hp.y0 = last1;
+		h.lp.x1 = h.lp.y1 = h.hp.x1 = h.hp.y1 = last2;
+		store_words(h, ss + (send * kMaxChannels + c) * 8 * kLanes);
+	}
+}
 
 // SF: the sends' shelf filters are compiled in (apply_filters, oalsfxpp.cpp:3101-3143): every stage filters the input
 // frame with ITS aux send's filters before the wet encode, stage 0 the direct send's as well, and the filter histories
@@ -55,6 +96,9 @@ __device__ __forceinline__ void stage(const MixArgs& a, Shared<CT>& sh, float* d
 	constexpr bool kReverb = std::is_same<Fx, FxReverb>::value;
 	constexpr bool kMod = std::is_same<Fx, FxModDelay>::value;
 	constexpr bool kEcho = std::is_same<Fx, FxEcho>::value;
+	constexpr int NC = CT ? CT : kMaxChannels;      // array extents
+	constexpr int CTD = CT ? CT : 1;                // divisor of the vector-store path (one and two channels only)
+	const int nch = CT ? CT : a.channels;
 	constexpr int HP = P > 0 ? P - 1 : 0;           // hand-off this stage reads
 	constexpr int HN = P < kMaxSlots - 1 ? P : 0;   // hand-off this stage writes (unless it is the last)
 	const bool last = P + 1 == a.relay_count;       // warp-uniform
@@ -63,16 +107,18 @@ __device__ __forceinline__ void stage(const MixArgs& a, Shared<CT>& sh, float* d
 	float* dst = a.dst + tile * a.io_ts + lane * a.io_ls;
 	uint32_t* ss = a.send_state + (static_cast<long long>(tile) * kSendStateWords) * kLanes + lane;
 	const int chunks = (a.frames + kChunk - 1) / kChunk;
-	const bool fast_out = a.io_cs == 1 && a.io_fs == CT && (a.frames % kChunk) == 0 && (a.io_ls % 4) == 0 &&
+	const bool fast_out = CT > 0 && a.io_cs == 1 && a.io_fs == CT && (a.frames % kChunk) == 0 && (a.io_ls % 4) == 0 &&
 		(a.io_ts % 4) == 0 && (reinterpret_cast<unsigned long long>(a.dst) & 15ULL) == 0;
 
 	SlotRunner<CT, SF, Fx> r;
 	float* win = dyn + a.relay_win[P];
-	SendHist dhist[SF ? CT : 1];   // stage 0: the direct send's filter histories
+	SendHist dhist[SF ? NC : 1];   // stage 0: the direct send's filter histories
 	if (SF && P == 0) {
 #pragma unroll
-		for (int c = 0; c < CT; ++c) {
-			load_words(dhist[c], ss + c * 8 * kLanes);
+		for (int c = 0; c < NC; ++c) {
+			if (CT || c < nch) {
+				load_words(dhist[SF ? c : 0], ss + c * 8 * kLanes);
+			}
 		}
 	}
 	r.begin(a, P, tile, lane, (kReverb || kMod) ? win + lane : kEcho ? win + lane + 2 * kLanes : nullptr);
@@ -85,22 +131,24 @@ __device__ __forceinline__ void stage(const MixArgs& a, Shared<CT>& sh, float* d
 	auto issue_input = [&](int frame) {
 		if (P == 0 && !kReverb) {
 			if (io_ok && frame < a.frames) {
-				const unsigned slot = win_s + static_cast<unsigned>((frame & (kFwSlots - 1)) * CT * kLanes * 4);
+				const unsigned slot = win_s + static_cast<unsigned>((frame & (kFwSlots - 1)) * NC * kLanes * 4);
 #pragma unroll
-				for (int c = 0; c < CT; ++c) {
-					cp_async_f32_s(slot + c * kLanes * 4, in + c * a.io_cs);
+				for (int c = 0; c < NC; ++c) {
+					if (CT || c < nch) {
+						cp_async_f32_s(slot + c * kLanes * 4, in + c * a.io_cs);
+					}
 				}
 			}
 			in += a.io_fs;
 		}
 	};
-	float nx[kChunk][CT];
+	float nx[kChunk][NC];
 	auto load_rows = [&](int first) {
 #pragma unroll
 		for (int f = 0; f < kChunk; ++f) {
 #pragma unroll
-			for (int c = 0; c < CT; ++c) {
-				nx[f][c] = (io_ok && first + f < a.frames) ? src[(first + f) * a.io_fs + c * a.io_cs] : 0.0F;
+			for (int c = 0; c < NC; ++c) {
+				nx[f][c] = (io_ok && (CT || c < nch) && first + f < a.frames) ? src[(first + f) * a.io_fs + c * a.io_cs] : 0.0F;
 			}
 		}
 	};
@@ -127,8 +175,10 @@ __device__ __forceinline__ void stage(const MixArgs& a, Shared<CT>& sh, float* d
 #pragma unroll
 			for (int f = 0; f < kChunk; ++f) {
 #pragma unroll
-				for (int c = 0; c < CT; ++c) {
-					sh.win_in[(first + f) & (kFwSlots - 1)][c][lane] = nx[f][c];
+				for (int c = 0; c < NC; ++c) {
+					if (CT || c < nch) {
+						sh.win_in[(first + f) & (kFwSlots - 1)][c][lane] = nx[f][c];
+					}
 				}
 			}
 			load_rows(first + kChunk);
@@ -141,7 +191,7 @@ __device__ __forceinline__ void stage(const MixArgs& a, Shared<CT>& sh, float* d
 		}
 		for (int f = 0; f < count; ++f) {
 			const int i = first + f;
-			float x[CT], acc[CT];
+			float x[NC], acc[NC];
 			if (!kReverb) {
 				r.fx.prefetch_next(a.slot[P]);
 				issue_input(i + kFwDepth);
@@ -150,37 +200,45 @@ __device__ __forceinline__ void stage(const MixArgs& a, Shared<CT>& sh, float* d
 			}
 			if (P == 0) {
 #pragma unroll
-				for (int c = 0; c < CT; ++c) {
-					x[c] = io_ok ? sh.win_in[i & (kFwSlots - 1)][c][lane] : 0.0F;
+				for (int c = 0; c < NC; ++c) {
+					x[c] = (io_ok && (CT || c < nch)) ? sh.win_in[i & (kFwSlots - 1)][c][lane] : 0.0F;
 					acc[c] = 0.0F;
 				}
 				// direct send (oalsfxpp.cpp:2924-2950); gains sanitized by the host
 #pragma unroll
-				for (int c = 0; c < CT; ++c) {
-					pan_add<CT, true>(acc, CT, a.direct.gains[c], SF ? send_filter_step(a.direct, dhist[SF ? c : 0], x[c]) : x[c]);
+				for (int c = 0; c < NC; ++c) {
+					if (CT || c < nch) {
+						pan_add<CT, true>(acc, nch, a.direct.gains[c], SF ? send_filter_step(a.direct, dhist[SF ? c : 0], x[c]) : x[c]);
+					}
 				}
 			} else {
 #pragma unroll
-				for (int c = 0; c < CT; ++c) {
-					x[c] = sh.xch[HP][b][f][c][lane];
-					acc[c] = sh.xch[HP][b][f][CT + c][lane];
+				for (int c = 0; c < NC; ++c) {
+					if (CT || c < nch) {
+						x[c] = sh.xch[HP][b][f][c][lane];
+						acc[c] = sh.xch[HP][b][f][NC + c][lane];
+					}
 				}
 			}
 			r.step(a, P, x, acc);
 			if (last && !fast_out) {
 				if (io_ok) {
 #pragma unroll
-					for (int c = 0; c < CT; ++c) {
-						dst[i * a.io_fs + c * a.io_cs] = acc[c];
+					for (int c = 0; c < NC; ++c) {
+						if (CT || c < nch) {
+							dst[i * a.io_fs + c * a.io_cs] = acc[c];
+						}
 					}
 				}
 			} else {
 #pragma unroll
-				for (int c = 0; c < CT; ++c) {
-					if (!last) {
-						sh.xch[P][b][f][c][lane] = x[c];
+				for (int c = 0; c < NC; ++c) {
+					if (CT || c < nch) {
+						if (!last) {
+							sh.xch[P][b][f][c][lane] = x[c];
+						}
+						sh.xch[P][b][f][NC + c][lane] = acc[c];
 					}
-					sh.xch[P][b][f][CT + c][lane] = acc[c];
 				}
 			}
 		}
@@ -191,8 +249,8 @@ __device__ __forceinline__ void stage(const MixArgs& a, Shared<CT>& sh, float* d
 #pragma unroll
 				for (int g = 0; g < kChunk * CT / 4; ++g) {
 					const int e0 = 4 * g; // element index within the chunk: frame = e / CT, channel = e % CT
-					__stcs(row + g, make_float4(sh.xch[P][b][(e0 + 0) / CT][CT + (e0 + 0) % CT][lane], sh.xch[P][b][(e0 + 1) / CT][CT + (e0 + 1) % CT][lane],
-						sh.xch[P][b][(e0 + 2) / CT][CT + (e0 + 2) % CT][lane], sh.xch[P][b][(e0 + 3) / CT][CT + (e0 + 3) % CT][lane]));
+					__stcs(row + g, make_float4(sh.xch[P][b][(e0 + 0) / CTD][NC + (e0 + 0) % CTD][lane], sh.xch[P][b][(e0 + 1) / CTD][NC + (e0 + 1) % CTD][lane],
+						sh.xch[P][b][(e0 + 2) / CTD][NC + (e0 + 2) % CTD][lane], sh.xch[P][b][(e0 + 3) / CTD][NC + (e0 + 3) % CTD][lane]));
 				}
 			}
 		} else if (P < kMaxSlots - 1) {
@@ -210,17 +268,19 @@ __device__ __forceinline__ void stage(const MixArgs& a, Shared<CT>& sh, float* d
 		r.end(a, P, tile, lane, nullptr, nullptr);   // effect state + this send's filter histories
 		if (P == 0) {
 #pragma unroll
-			for (int c = 0; c < CT; ++c) {
-				store_words(dhist[c], ss + c * 8 * kLanes);
+			for (int c = 0; c < NC; ++c) {
+				if (CT || c < nch) {
+					store_words(dhist[SF ? c : 0], ss + c * 8 * kLanes);
+				}
 			}
 		}
 		return;
 	}
 	r.end_state_only(a, P, tile, lane);
 	if (P == 0) {
-		duo::store_passthrough_history<CT>(ss, 0, src, a, io_ok);
+		store_passthrough_history<CT>(ss, 0, src, a, io_ok);
 	}
-	duo::store_passthrough_history<CT>(ss, 1 + a.aux_index[P], src, a, io_ok);
+	store_passthrough_history<CT>(ss, 1 + a.aux_index[P], src, a, io_ok);
 }
 
 template <int CT, bool HEAVY, int P, bool SF>
@@ -246,8 +306,9 @@ __device__ __forceinline__ void dispatch(const MixArgs& a, Shared<CT>& sh, float
 template <int CT, bool HEAVY, bool SF = false>
 __device__ __forceinline__ void relay_body(const MixArgs& a)
 {
-	extern __shared__ __align__(16) float dyn[];
-	__shared__ __align__(16) Shared<CT> sh;
+	extern __shared__ __align__(16) float dyn_base[];
+	float* dyn = dyn_base;
+	Shared<CT>& sh = SharedPlace<CT>::get(dyn);
 	const int tile = a.tiles ? static_cast<int>(a.tiles[blockIdx.x].tile) : a.tile_first + static_cast<int>(blockIdx.x);
 	const int lane = threadIdx.x % kLanes;
 	// Warp w of every CTA lands on scheduler w: rotate the stages so each scheduler sees all of them.

@@ -99,6 +99,13 @@ def main():
             [T.eax_reverb, T.chorus, T.reverb, T.compressor], 416),
         run("relay: distortion+flanger+equalizer, 65536 stereo streams", 65536, F.stereo, 48000,
             [T.distortion, T.flanger, T.equalizer], 32, blocks=10, warm=3),
+        # more than two channels / active send shelf filters: the wide and the filter-carrying relay kernels, one launch
+        # (OALSFX_KERNEL=generic gives the former path: one exact pass per slot)
+        run("relay wide: cfg4 chain on 5.1, 65536 streams", 65536, F.five_point_one, 48000,
+            [T.equalizer, T.chorus, T.echo, T.eax_reverb], 268, blocks=8, warm=3),
+        run("relay sf: cfg4 chain, stereo, send shelf filters active, 65536 streams", 65536, F.stereo, 48000,
+            [T.equalizer, T.chorus, T.echo, T.eax_reverb], 236, blocks=8, warm=3,
+            setup=lambda eng: eng.set_sends(direct=(0.8, 0.5, 1.0), aux=[(0.7, 1.0, 0.4), (1.0, 1.0, 1.0), (1.0, 0.25, 0.5), (0.9, 0.3, 0.6)])),
         # every stream its own reverb preset (113 parameter classes): table mode, coefficient blocks from HBM
         run("table mode: cfg4 chain, 113 reverb presets over 16384 stereo streams", 16384, F.stereo, 48000,
             [T.equalizer, T.chorus, T.echo, T.eax_reverb], 236, blocks=10, warm=3, setup=all_presets),

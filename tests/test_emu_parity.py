@@ -173,7 +173,7 @@ def _gpu_scenarios(monkeypatch):
     return G
 
 
-@pytest.mark.parametrize("sig", [0, 1, 2, 6])
+@pytest.mark.parametrize("sig", [0, 1, 2, 6, 8, 10])
 def test_relay_selection_and_slot_compaction(checker, sig, monkeypatch):
     _gpu_scenarios(monkeypatch).test_relay_pipeline_runs_any_signature_in_one_launch(checker, sig)
 
@@ -243,6 +243,6 @@ def test_waveshaper_expectation(monkeypatch):
     _gpu_scenarios(monkeypatch).test_waveshaper_divisions_are_ieee_divisions()
 
 
-@pytest.mark.parametrize("case", ["chain-stereo", "echo-mono"])
+@pytest.mark.parametrize("case", ["chain-stereo", "echo-mono", "chain-5.1"])
 def test_send_filter_relay_selection(checker, case, monkeypatch):
     _gpu_scenarios(monkeypatch).test_send_shelf_filters_run_in_one_launch(checker, case)

@@ -598,15 +598,16 @@ def test_waveshaper_divisions_are_ieee_divisions():
                 _assert_match(x, got, True, f"edge coefficient {fc}, input set {i}")
 
 
-@pytest.mark.parametrize("case", ["chain-stereo", "echo-mono", "reverb-eq-stereo"])
+@pytest.mark.parametrize("case", ["chain-stereo", "echo-mono", "reverb-eq-stereo", "chain-5.1", "flanger-7.1"])
 def test_send_shelf_filters_run_in_one_launch(checker, case):
     """Active send shelf filters (apply_filters, oalsfxpp.cpp:3101-3143) used to drop a group to one exact pass per slot;
     the relay pipeline now carries them (relay_sf_kernel: every stage filters the input with its own send's filters, the
     histories are state): one launch per block, bit-exact, also when the send settings change between blocks."""
     lib = _lib()
-    fmt = F.mono if case == "echo-mono" else F.stereo
+    fmt = {"echo-mono": F.mono, "chain-5.1": F.five_point_one, "flanger-7.1": F.seven_point_one}.get(case, F.stereo)
     slots = {"chain-stereo": [T.equalizer, T.chorus, T.echo, T.eax_reverb], "echo-mono": [T.echo],
-             "reverb-eq-stereo": [T.eax_reverb, T.null, T.equalizer]}[case]
+             "reverb-eq-stereo": [T.eax_reverb, T.null, T.equalizer], "chain-5.1": [T.equalizer, T.chorus, T.echo, T.eax_reverb],
+             "flanger-7.1": [T.flanger, T.compressor]}[case]
     sends_a = {-1: (0.8, 0.5, 1.0), 0: (0.7, 1.0, 0.4), 2: (1.0, 0.25, 0.5)}
     sends_b = {-1: (1.0, 1.0, 0.3), 0: (0.9, 0.3, 0.6)}
     S, blocks = 70, [1024, 333, 1024, 2, 640]
@@ -698,6 +699,12 @@ RELAY_SIGNATURES = [
     (F.mono, 96000, [T.equalizer, T.distortion, T.compressor, T.dedicated_low_frequency]),
     (F.mono, 48000, [T.null, T.reverb, T.echo, T.flanger]),
     (F.stereo, 48000, [T.compressor, T.equalizer, T.null, T.null]),
+    # more than two device channels: the relay kernels with a run-time channel count (index 8 ..)
+    (F.five_point_one, 48000, [T.equalizer, T.chorus, T.echo, T.eax_reverb]),    # BASELINE's chain on 5.1
+    (F.quad, 44100, [T.echo, T.eax_reverb]),
+    (F.seven_point_one, 48000, [T.flanger, T.null, T.distortion, T.compressor]),
+    (F.six_point_one, 48000, [T.reverb, T.dedicated_dialog, T.equalizer, T.ring_modulator]),
+    (F.five_point_one_rear, 96000, [T.chorus, T.echo]),
 ]
 
 
@@ -709,7 +716,7 @@ def test_relay_pipeline_runs_any_signature_in_one_launch(checker, sig):
     (ring modulator: device sinf, 1e-5)."""
     fmt, rate, slots = RELAY_SIGNATURES[sig]
     lib = _lib()
-    C = 1 if fmt == F.mono else 2
+    C = ox.channel_count(fmt)
     S, blocks = 70, [1024, 333, 1024, 2, 641]
     total = sum(blocks)
     x = np.stack([H.noise(900 + 10 * sig + s, C, total) for s in range(S)])
@@ -747,6 +754,7 @@ def test_relay_pipeline_runs_any_signature_in_one_launch(checker, sig):
             y[:, at:at + n] = eng.mix(np.ascontiguousarray(x[:, at:at + n]))
             at += n
         assert eng.launch_count == len(blocks), eng.launch_count
+        assert eng.last_kernel.startswith("kRelayWide" if C > 2 else "kRelay"), eng.last_kernel
     exact = T.ring_modulator not in slots
     for s in (0, 31, 32, 63, 64, S - 1):
         expect = H.run_script_orc(checker, fmt, rate, len(slots), script, x[s])
