@@ -142,7 +142,7 @@ struct FxReverbT {
 	const float* pf_cur;
 	bool primed, can_pf;
 	int32_t pf_row4;   // window row of the first position of the batch holding the current position
-	bool pan_static;   // this sub-chunk: no gain ramps and every one of the 8 x C pan gains is audible
+	bool pan_static;   // this sub-chunk: no gain ramps and every one of the 8 x C pan gains is audible or an exact zero
 	bool pan_ramp_all; // this sub-chunk: every one of this instance's pan gains ramps (a gain change: all of them scale)
 	uint32_t direct_groups; // this sub-chunk: tap groups (bit = OLD-tap group id) the window cannot serve, read in place
 
@@ -296,7 +296,10 @@ struct FxReverbT {
 						pan_ramp_all = false;
 						if (audible(gain)) {
 							active_mask[l >> 2] |= bit;
-						} else {
+						} else if (gain != 0.0F) {
+							// (an inaudible gain that is an exact zero -- the LFE column of every 5.1 / 6.1 / 7.1 pan -- keeps
+							// the static path: its product is +-0, and adding that changes nothing: the bus starts at +0 and
+							// never becomes -0; finite samples assumed, as for the host's sanitized gains, fx.cuh pan_add)
 							pan_static = false;
 						}
 					}
