@@ -83,6 +83,18 @@ def all_presets(eng):
         k += 1
 
 
+_PRESETS = []
+
+
+def rotate_presets(eng, b):
+    """Every tile (32 streams) its own reverb preset, and every one of them a different preset each block: the whole
+    property set changes, so every class is re-derived, the class table re-uploaded, and every stream cross-fades."""
+    if not _PRESETS:
+        _PRESETS.extend(ox.reverb_preset(g, n) for g, n in ox.reverb_preset_names())
+    for c in range(eng.num_streams // 32):
+        eng.set_effect(3, T.eax_reverb, _PRESETS[(c + b) % len(_PRESETS)], first_stream=c * 32, n_streams=32)
+
+
 def main():
     out = [
         run("cfg1: EAX reverb, 1024 mono streams", 1024, F.mono, 48000, [T.eax_reverb], 200),
@@ -116,6 +128,12 @@ def main():
                    [T.equalizer, T.chorus, T.echo, T.eax_reverb], 236, blocks=10, warm=3, setup=all_presets))
     out.append(run("class per tile: cfg4 chain, 113 reverb presets in runs of 32 over 65536 stereo streams", 65536, F.stereo, 48000,
                    [T.equalizer, T.chorus, T.echo, T.eax_reverb], 236, blocks=10, warm=3, setup=all_presets))
+    # ... and all of them changing every block (`host_param_update_ms_per_block` = the set_effect calls from Python; the
+    # derivation of the dirty classes and the table upload are inside the mix call, i.e. inside ms_per_block_device)
+    out.append(run("class per tile: cfg4 chain, 512 classes over 16384 stereo streams, every class a new preset every block", 16384, F.stereo, 48000,
+                   [T.equalizer, T.chorus, T.echo, T.eax_reverb], 236, schedule=rotate_presets, blocks=10, warm=3))
+    out.append(run("class per tile: cfg4 chain, 4096 classes over 131072 stereo streams, every class a new preset every block", 131072, F.stereo, 48000,
+                   [T.equalizer, T.chorus, T.echo, T.eax_reverb], 236, schedule=rotate_presets, blocks=6, warm=3))
     print(json.dumps({"gpu": torch.cuda.get_device_name(0), "block_frames": BLOCK, "results": out}, indent=1))
 
 
