@@ -37,7 +37,12 @@
 namespace oalsfx {
 namespace relay {
 
-constexpr int kChunk = 4;                 // frames per hand-off (= the output row batch)
+#ifndef OALSFX_RELAY_CHUNK
+#define OALSFX_RELAY_CHUNK 4
+#endif
+constexpr int kChunk = 4;                 // frames per hand-off of the wide kernels (their exchange is 68 KB as it is)
+template <int CT>
+struct ChunkOf { static constexpr int value = CT ? OALSFX_RELAY_CHUNK : kChunk; }; // frames per hand-off (a multiple of the output row batch of 4)
 constexpr int kThreads = kMaxSlots * kLanes;
 
 // CT = 0: the device channel count is a run-time value (quad, 5.1, 6.1, 7.1: MixArgs::channels), arrays are sized for
@@ -45,8 +50,10 @@ constexpr int kThreads = kMaxSlots * kLanes;
 template <int CT>
 struct Shared {
 	static constexpr int NC = CT ? CT : kMaxChannels;
-	float xch[kMaxSlots][2][kChunk][2 * NC][kLanes]; // hand-off P -> P+1: x_0..x_C-1, bus_0..bus_C-1 (the last stage parks finished frames in its own)
-	float win_in[kFwSlots][NC][kLanes];              // stage 0: input frames in flight
+	static constexpr int K = ChunkOf<CT>::value;
+	static constexpr int WIN = K > kFwSlots ? K : kFwSlots; // (a reverb in stage 0 parks a whole hand-off of input frames here)
+	float xch[kMaxSlots][2][K][2 * NC][kLanes];      // hand-off P -> P+1: x_0..x_C-1, bus_0..bus_C-1 (the last stage parks finished frames in its own)
+	float win_in[WIN][NC][kLanes];                   // stage 0: input frames in flight
 };
 
 // Where the exchange lives: static shared memory for one and two channels (16 / 28 KB), the head of the dynamic
@@ -97,6 +104,8 @@ __device__ __forceinline__ void stage(const MixArgs& a, Shared<CT>& sh, float* d
 	constexpr bool kMod = std::is_same<Fx, FxModDelay>::value;
 	constexpr bool kEcho = std::is_same<Fx, FxEcho>::value;
 	constexpr int NC = CT ? CT : kMaxChannels;      // array extents
+	constexpr int kChunk = ChunkOf<CT>::value;      // frames per hand-off
+	constexpr int kWinMask = (kReverb ? Shared<CT>::WIN : kFwSlots) - 1;
 	constexpr int CTD = CT ? CT : 1;                // divisor of the vector-store path (one and two channels only)
 	const int nch = CT ? CT : a.channels;
 	constexpr int HP = P > 0 ? P - 1 : 0;           // hand-off this stage reads
@@ -177,7 +186,7 @@ __device__ __forceinline__ void stage(const MixArgs& a, Shared<CT>& sh, float* d
 #pragma unroll
 				for (int c = 0; c < NC; ++c) {
 					if (CT || c < nch) {
-						sh.win_in[(first + f) & (kFwSlots - 1)][c][lane] = nx[f][c];
+						sh.win_in[(first + f) & kWinMask][c][lane] = nx[f][c];
 					}
 				}
 			}
@@ -201,7 +210,7 @@ __device__ __forceinline__ void stage(const MixArgs& a, Shared<CT>& sh, float* d
 			if (P == 0) {
 #pragma unroll
 				for (int c = 0; c < NC; ++c) {
-					x[c] = (io_ok && (CT || c < nch)) ? sh.win_in[i & (kFwSlots - 1)][c][lane] : 0.0F;
+					x[c] = (io_ok && (CT || c < nch)) ? sh.win_in[i & kWinMask][c][lane] : 0.0F;
 					acc[c] = 0.0F;
 				}
 				// direct send (oalsfxpp.cpp:2924-2950); gains sanitized by the host
@@ -246,6 +255,7 @@ __device__ __forceinline__ void stage(const MixArgs& a, Shared<CT>& sh, float* d
 			if (fast_out && io_ok) {
 				// kChunk frames x CT channels of this thread's row, 16 bytes at a time (own column: no barrier)
 				float4* row = reinterpret_cast<float4*>(dst + first * CT);
+				static_assert(kChunk % 4 == 0, "output rows are written four frames at a time");
 #pragma unroll
 				for (int g = 0; g < kChunk * CT / 4; ++g) {
 					const int e0 = 4 * g; // element index within the chunk: frame = e / CT, channel = e % CT
