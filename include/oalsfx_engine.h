@@ -163,6 +163,22 @@ int oalsfx_effect_normalize(int effect_type, void* props, size_t props_bytes);
 int oalsfx_reverb_preset(const char* group, const char* name, void* props, size_t props_bytes);
 const char* oalsfx_reverb_preset_name(int index);
 
+/* Stream placement for many parameter sets.  The engine runs a 32-stream tile at the fused kernels' speed
+ * when all of its streams share one parameter set ("class"); a tile of mixed classes takes table mode, ~15x slower per
+ * stream.  A host that owns many voices with arbitrary presets decides the ORDER of its streams in the engine -- each
+ * stream is an independent row of the mix buffers, as each Api instance of the reference has its own buffer
+ * (oalsfxpp.cpp:2820-2827) -- and this helper computes an order that keeps every tile class-pure: given one label per
+ * caller stream (equal labels = the same settings in every slot and send), classes are laid out one after the other in
+ * order of first appearance, each padded to a multiple of 32; streams of a class keep their relative order.
+ * engine_index_of_stream[s] receives the engine stream index of caller stream s.  Returns the number of engine streams to
+ * create (>= n_streams; indices nobody was assigned are silent streams: feed zeros, ignore their output), or a negative
+ * OALSFX_ERR_* code.  class_triples / class_count are optional: with class_capacity > 0, up to class_capacity triples
+ * (label, first engine index, length of the class's range INCLUDING its padding streams: a multiple of 32) are written,
+ * so that one oalsfx_engine_set_effect call per class configures its whole range -- the padding streams must carry their
+ * tile's settings, or the tile is a mixed one again. */
+long long oalsfx_plan_placement(const int32_t* class_of_stream, int n_streams, int32_t* engine_index_of_stream,
+	int32_t* class_triples, int class_capacity, int* class_count);
+
 /* Library build identification, e.g. "oalsfx_b200 sm_100a cuda". */
 const char* oalsfx_build_info(void);
 

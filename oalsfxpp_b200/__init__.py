@@ -9,11 +9,11 @@ processing of its own and there is no CPU fallback: importing works anywhere, bu
 from .props import (ChannelFormat, EffectType, EffectProps, channel_count, default_props,
                     normalize_props, reverb_preset, reverb_preset_names)
 from .engine import (Engine, OalsfxError, LAYOUT_STREAM_MAJOR, LAYOUT_TILED, SPACE_HOST,
-                     SPACE_DEVICE, library_path, load_library, build_info)
+                     SPACE_DEVICE, library_path, load_library, build_info, plan_placement)
 
 __all__ = [
     "ChannelFormat", "EffectType", "EffectProps", "channel_count", "default_props",
     "normalize_props", "reverb_preset", "reverb_preset_names", "Engine", "OalsfxError",
     "LAYOUT_STREAM_MAJOR", "LAYOUT_TILED", "SPACE_HOST", "SPACE_DEVICE", "library_path",
-    "load_library", "build_info",
+    "load_library", "build_info", "plan_placement",
 ]

@@ -1681,6 +1681,49 @@ int oalsfx_reverb_preset(const char* group, const char* name, void* props, size_
 	return OALSFX_ERR_ARGUMENT;
 }
 
+long long oalsfx_plan_placement(const int32_t* class_of_stream, int n_streams, int32_t* engine_index_of_stream,
+	int32_t* class_triples, int class_capacity, int* class_count)
+{
+	if (!class_of_stream || !engine_index_of_stream || n_streams < 1 || class_capacity < 0 || (class_capacity > 0 && !class_triples)) {
+		return OALSFX_ERR_ARGUMENT;
+	}
+	// classes in order of first appearance, with their stream counts
+	std::map<int32_t, int> slot_of_label;
+	std::vector<int32_t> labels;
+	std::vector<long long> count;
+	for (int s = 0; s < n_streams; ++s) {
+		auto it = slot_of_label.find(class_of_stream[s]);
+		if (it == slot_of_label.end()) {
+			it = slot_of_label.emplace(class_of_stream[s], static_cast<int>(labels.size())).first;
+			labels.push_back(class_of_stream[s]);
+			count.push_back(0);
+		}
+		++count[static_cast<size_t>(it->second)];
+	}
+	// every class starts on a tile boundary
+	std::vector<long long> next(labels.size());
+	long long at = 0;
+	for (size_t c = 0; c < labels.size(); ++c) {
+		next[c] = at;
+		if (static_cast<int>(c) < class_capacity) {
+			class_triples[3 * c + 0] = labels[c];
+			class_triples[3 * c + 1] = static_cast<int32_t>(at);
+			class_triples[3 * c + 2] = static_cast<int32_t>((count[c] + kLanes - 1) / kLanes * kLanes);
+		}
+		at += (count[c] + kLanes - 1) / kLanes * kLanes;
+		if (at > 0x7FFFFFFFLL) {
+			return OALSFX_ERR_ARGUMENT;
+		}
+	}
+	for (int s = 0; s < n_streams; ++s) {
+		engine_index_of_stream[s] = static_cast<int32_t>(next[static_cast<size_t>(slot_of_label[class_of_stream[s]])]++);
+	}
+	if (class_count) {
+		*class_count = static_cast<int>(labels.size());
+	}
+	return at;
+}
+
 const char* oalsfx_reverb_preset_name(int index)
 {
 	return (index >= 0 && index < kPresetCount) ? kPresets[index].full : nullptr;

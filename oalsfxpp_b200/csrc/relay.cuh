@@ -82,15 +82,15 @@ __device__ __forceinline__ void store_passthrough_history(uint32_t* ss, int send
 {
 	if (CT) {
 		duo::store_passthrough_history<CT ? CT : 1>(ss, send, src, a, io_ok);
-		return;
-	}
-	for (int c = 0; c < a.channels; ++c) {
-		const float last1 = io_ok ? src[(a.frames - 1) * a.io_fs + c * a.io_cs] : 0.0F;
-		const float last2 = io_ok ? src[(a.frames - 2) * a.io_fs + c * a.io_cs] : 0.0F;
-		SendHist h;
-		h.lp.x0 = h.lp.y0 = h.hp.x0 = h.hp.y0 = last1;
-		h.lp.x1 = h.lp.y1 = h.hp.x1 = h.hp.y1 = last2;
-		store_words(h, ss + (send * kMaxChannels + c) * 8 * kLanes);
+	} else {
+		for (int c = 0; c < a.channels; ++c) {
+			const float last1 = io_ok ? src[(a.frames - 1) * a.io_fs + c * a.io_cs] : 0.0F;
+			const float last2 = io_ok ? src[(a.frames - 2) * a.io_fs + c * a.io_cs] : 0.0F;
+			SendHist h;
+			h.lp.x0 = h.lp.y0 = h.hp.x0 = h.hp.y0 = last1;
+			h.lp.x1 = h.lp.y1 = h.hp.x1 = h.hp.y1 = last2;
+			store_words(h, ss + (send * kMaxChannels + c) * 8 * kLanes);
+		}
 	}
 }
 

@@ -85,6 +85,8 @@ def bind(lib):
     lib.oalsfx_pcm_to_float.restype = i32
     lib.oalsfx_debug_waveshaper.argtypes = [vp, vp, C.c_float, vp, C.c_longlong, vp]
     lib.oalsfx_debug_waveshaper.restype = i32
+    lib.oalsfx_plan_placement.argtypes = [vp, i32, vp, vp, i32, vp]
+    lib.oalsfx_plan_placement.restype = C.c_longlong
     lib.oalsfx_float_to_s16.argtypes = [vp, vp, vp, i32, C.c_longlong, vp, vp]
     lib.oalsfx_float_to_s16.restype = i32
     lib.oalsfx_engine_snapshot_size.argtypes = [vp]
@@ -100,7 +102,7 @@ EXPORTED_SYMBOLS = (
     "oalsfx_engine_create", "oalsfx_engine_destroy", "oalsfx_engine_set_effect",
     "oalsfx_engine_set_sends", "oalsfx_engine_mix", "oalsfx_engine_mix_bus", "oalsfx_engine_reduce_bus",
     "oalsfx_engine_pin_host", "oalsfx_engine_unpin_host",
-    "oalsfx_engine_debug_state", "oalsfx_debug_waveshaper", "oalsfx_engine_launch_count", "oalsfx_engine_last_kernel", "oalsfx_engine_device_bytes",
+    "oalsfx_engine_debug_state", "oalsfx_debug_waveshaper", "oalsfx_plan_placement", "oalsfx_engine_launch_count", "oalsfx_engine_last_kernel", "oalsfx_engine_device_bytes",
     "oalsfx_last_error", "oalsfx_build_info", "oalsfx_effect_defaults", "oalsfx_effect_normalize",
     "oalsfx_reverb_preset", "oalsfx_reverb_preset_name", "oalsfx_pcm_to_float", "oalsfx_float_to_s16",
     "oalsfx_engine_snapshot_size", "oalsfx_engine_snapshot", "oalsfx_engine_restore",
@@ -119,6 +121,21 @@ def load_library():
                                   "the engine has no CPU fallback")
         _LIB = bind(C.CDLL(path))
     return _LIB
+
+
+def plan_placement(labels, lib=None):
+    """oalsfx_plan_placement: an engine stream index per caller stream such that every 32-stream tile holds one class.
+    Returns (index array, engine stream count, [(label, first engine index, range length incl. padding), ...])."""
+    lib = lib or load_library()
+    labels = np.ascontiguousarray(labels, dtype=np.int32)
+    index = np.empty(labels.size, dtype=np.int32)
+    triples = np.empty((max(1, labels.size), 3), dtype=np.int32)
+    n_classes = C.c_int(0)
+    total = lib.oalsfx_plan_placement(labels.ctypes.data, int(labels.size), index.ctypes.data, triples.ctypes.data,
+                                      int(triples.shape[0]), C.addressof(n_classes))
+    if total < 0:
+        raise OalsfxError(int(total), "oalsfx_plan_placement: bad arguments")
+    return index, int(total), [tuple(int(v) for v in t) for t in triples[:n_classes.value]]
 
 
 def build_info(lib=None):

@@ -128,6 +128,20 @@ def main():
                    [T.equalizer, T.chorus, T.echo, T.eax_reverb], 236, blocks=10, warm=3, setup=all_presets))
     out.append(run("class per tile: cfg4 chain, 113 reverb presets in runs of 32 over 65536 stereo streams", 65536, F.stereo, 48000,
                    [T.equalizer, T.chorus, T.echo, T.eax_reverb], 236, blocks=10, warm=3, setup=all_presets))
+    # arbitrary assignment (stream s -> preset s mod 113: every tile would hold 32 classes) ordered by oalsfx_plan_placement:
+    # class-pure tiles, one launch; the engine is created with the padded stream count and the padding streams are processed
+    for users in (16384, 65536):
+        index, total, classes = ox.plan_placement(np.arange(users, dtype=np.int32) % 113)
+        per = [ox.reverb_preset(g, n) for g, n in ox.reverb_preset_names()]
+
+        def place(eng, classes=classes, per=per):
+            for label, first, span in classes:
+                eng.set_effect(3, T.eax_reverb, per[label % len(per)], first_stream=first, n_streams=span)
+
+        r = run("placed: cfg4 chain, 113 reverb presets arbitrarily assigned over %d stereo streams, ordered by oalsfx_plan_placement (%d engine streams)" % (users, total),
+                total, F.stereo, 48000, [T.equalizer, T.chorus, T.echo, T.eax_reverb], 236, blocks=10, warm=3, setup=place)
+        r["caller_streams"] = users
+        out.append(r)
     # ... and all of them changing every block (`host_param_update_ms_per_block` = the set_effect calls from Python; the
     # derivation of the dirty classes and the table upload are inside the mix call, i.e. inside ms_per_block_device)
     out.append(run("class per tile: cfg4 chain, 512 classes over 16384 stereo streams, every class a new preset every block", 16384, F.stereo, 48000,

@@ -237,6 +237,10 @@ def test_mix_bus_host_logic():
         assert np.max(np.abs(bus - want)) <= 1e-5 * np.sqrt(streams)
 
 
+def test_placement_helper_and_class_per_tile_selection(checker, monkeypatch):
+    _gpu_scenarios(monkeypatch).test_placement_keeps_arbitrary_presets_on_the_class_per_tile_launch(checker)
+
+
 def test_waveshaper_expectation(monkeypatch):
     """The waveshaper scenario of the GPU suite on the CPU backend (the `/` operator): pins the numpy formula the GPU's
     batched division is held against."""

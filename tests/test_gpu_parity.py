@@ -554,6 +554,49 @@ def test_span_kernel_every_tile_share(checker, tiles):
         _assert_match(expect, per[0, k].cpu().numpy(), True, f"span share, {tiles} tiles, input {k}")
 
 
+def test_placement_keeps_arbitrary_presets_on_the_class_per_tile_launch(checker):
+    """f1: every voice its own preset in no particular order.  Left in the caller's order the tiles hold mixed classes
+    (table mode); ordered by oalsfx_plan_placement every tile is class-pure, one set_effect call per class covers its
+    contiguous range, and a block is ONE class-per-tile launch.  Bit-exact per caller stream; the padding streams are
+    silent."""
+    lib = _lib()
+    names = ox.reverb_preset_names(lib=lib)
+    n_user, n_presets, blocks = 700, 23, [1024, 333]
+    labels = np.array([(s * 7 + s // 50) % n_presets for s in range(n_user)], dtype=np.int32)
+    index, total, classes = ox.plan_placement(labels, lib=lib)
+    assert len(classes) == n_presets and total % 32 == 0 and total >= n_user
+    assert len(set(index.tolist())) == n_user and index.max() < total
+    for label, first, span in classes:
+        members = np.nonzero(labels == label)[0]
+        assert span == (len(members) + 31) // 32 * 32 and first % 32 == 0
+        assert np.array_equal(index[members], first + np.arange(len(members)))   # contiguous, caller order kept
+    frames = sum(blocks)
+    x_user = np.stack([H.noise(7000 + s, 2, frames) for s in range(n_user)])
+    x = np.zeros((total, frames, 2), dtype=np.float32)
+    x[index] = x_user
+    y = np.empty_like(x)
+    chain = [T.equalizer, T.chorus, T.echo]
+    props = {label: ox.reverb_preset(*names[(label * 5) % len(names)], lib=lib) for label, _, _ in classes}
+    with ox.Engine(total, F.stereo, 48000, 4, lib=lib) as eng:
+        for i, t in enumerate(chain):
+            eng.set_effect(i, t)
+        for label, first, span in classes:                       # (padding streams included: they share their tile's class)
+            eng.set_effect(3, T.eax_reverb, props[label], first_stream=first, n_streams=span)
+        at = 0
+        for n in blocks:
+            before = eng.launch_count
+            y[:, at:at + n] = eng.mix(np.ascontiguousarray(x[:, at:at + n]))
+            assert eng.launch_count - before == 1 and eng.last_kernel == "kMultiChainStereo", (eng.launch_count - before, eng.last_kernel)
+            at += n
+    for s in (0, 1, 49, 50, 333, n_user - 1):
+        script = H.simple_script([(t, None) for t in chain] + [(T.eax_reverb, props[int(labels[s])])], blocks)
+        expect = H.run_script_orc(checker, F.stereo, 48000, 4, script, x_user[s])
+        _assert_match(expect, y[index[s]], True, f"caller stream {s}")
+    used = np.zeros(total, dtype=bool)
+    used[index] = True
+    assert not y[~used].any()
+
+
 def test_waveshaper_divisions_are_ieee_divisions():
     """The distortion stage runs its twelve divisions per sample (oalsfxpp.cpp:4720-4722) as a batched correctly-rounded
     sequence behind one guard instead of through the `/` operator (fx.cuh, FxDistortion::shape).  Bit for bit against
