@@ -28,21 +28,21 @@ bool launch_relay_family(int kernel_id, const MixArgs& args, cudaStream_t st)
 #define OALSFX_RX(id, CT, HEAVY) \
 	case id: \
 		relay_attributes(done[id], relay::relay_kernel<CT, HEAVY>, exchange_bytes<CT>()); \
-		relay::relay_kernel<CT, HEAVY><<<static_cast<unsigned>(args.tile_count), relay::kThreads, dyn + exchange_bytes<CT>(), st>>>(args); \
+		relay::relay_kernel<CT, HEAVY><<<static_cast<unsigned>(args.tile_count), static_cast<unsigned>(kLanes * args.relay_count), dyn + exchange_bytes<CT>(), st>>>(args); \
 		return true;
 		OALSFX_RELAY_TABLE(OALSFX_RX)
 #undef OALSFX_RX
 #define OALSFX_RX(id, CT, HEAVY) \
 	case id: \
 		relay_attributes(done[id], relay::relay_multi_kernel<CT, HEAVY>, exchange_bytes<CT>()); \
-		relay::relay_multi_kernel<CT, HEAVY><<<static_cast<unsigned>(args.tile_count), relay::kThreads, dyn + exchange_bytes<CT>(), st>>>(args); \
+		relay::relay_multi_kernel<CT, HEAVY><<<static_cast<unsigned>(args.tile_count), static_cast<unsigned>(kLanes * args.relay_count), dyn + exchange_bytes<CT>(), st>>>(args); \
 		return true;
 		OALSFX_RELAY_MULTI_TABLE(OALSFX_RX)
 #undef OALSFX_RX
 #define OALSFX_RX(id, CT, HEAVY) \
 	case id: \
 		relay_attributes(done[id], relay::relay_sf_kernel<CT, HEAVY>, exchange_bytes<CT>()); \
-		relay::relay_sf_kernel<CT, HEAVY><<<static_cast<unsigned>(args.tile_count), relay::kThreads, dyn + exchange_bytes<CT>(), st>>>(args); \
+		relay::relay_sf_kernel<CT, HEAVY><<<static_cast<unsigned>(args.tile_count), static_cast<unsigned>(kLanes * args.relay_count), dyn + exchange_bytes<CT>(), st>>>(args); \
 		return true;
 		OALSFX_RELAY_SF_TABLE(OALSFX_RX)
 #undef OALSFX_RX

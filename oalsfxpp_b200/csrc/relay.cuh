@@ -321,11 +321,10 @@ __device__ __forceinline__ void relay_body(const MixArgs& a)
 	Shared<CT>& sh = SharedPlace<CT>::get(dyn);
 	const int tile = a.tiles ? static_cast<int>(a.tiles[blockIdx.x].tile) : a.tile_first + static_cast<int>(blockIdx.x);
 	const int lane = threadIdx.x % kLanes;
-	// Warp w of every CTA lands on scheduler w: rotate the stages so each scheduler sees all of them.
-	const int st = (static_cast<int>(threadIdx.x / kLanes) + static_cast<int>(blockIdx.x)) & (kMaxSlots - 1);
-	if (st >= a.relay_count) {
-		return;
-	}
+	// A CTA has one warp per stage (the launch gives it 32 x relay_count threads: a two-stage signature then holds half
+	// the registers of a four-stage one, and twice the CTAs fit an SM).  Warp w of every CTA lands on scheduler w:
+	// rotate the stages so each scheduler sees all of them.
+	const int st = (static_cast<int>(threadIdx.x / kLanes) + static_cast<int>(blockIdx.x)) % a.relay_count;
 	switch (st) {
 	case 0: dispatch<CT, HEAVY, 0, SF>(a, sh, dyn, tile, lane); break;
 	case 1: dispatch<CT, HEAVY, 1, SF>(a, sh, dyn, tile, lane); break;
@@ -359,12 +358,12 @@ __global__ void __launch_bounds__(kThreads, HEAVY ? 2 : 4) relay_multi_kernel(co
 	uint32_t* ps = reinterpret_cast<uint32_t*>(&sa);
 	constexpr int kWords = static_cast<int>(sizeof(MixArgs) / 4), kCoef0 = static_cast<int>(kMixCoefOffset / 4),
 		kCoefWords = static_cast<int>(kMixCoefBytes / 4);
-	for (int i = threadIdx.x; i < kWords; i += kThreads) {
+	for (int i = threadIdx.x; i < kWords; i += static_cast<int>(blockDim.x)) {
 		if (i < kCoef0 || i >= kCoef0 + kCoefWords) {
 			ps[i] = pa[i];
 		}
 	}
-	for (int i = threadIdx.x; i < kCoefWords; i += kThreads) {
+	for (int i = threadIdx.x; i < kCoefWords; i += static_cast<int>(blockDim.x)) {
 		ps[kCoef0 + i] = entry->coefs[i];
 	}
 	__syncthreads();
