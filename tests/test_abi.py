@@ -59,3 +59,21 @@ def test_pod_layout_matches_reference(ref):
     assert ref.orc_sizeof_effect() == 112
     shim = H.api_shim("emu")
     assert shim.orc_sizeof_effect_props() == 108 and shim.orc_sizeof_effect() == 112
+
+
+def test_plan_placement_is_a_pure_host_function():
+    """oalsfx_plan_placement needs no engine and no device: callable on the PRODUCT library without a GPU.  Classes in
+    order of first appearance, each range a multiple of 32, caller order kept inside a class; bad arguments are refused."""
+    import numpy as np
+    import oalsfxpp_b200 as ox
+    lib = E.bind(ctypes.CDLL(E.library_path()))
+    labels = np.array([7, 7, 3, 7, 3, 9] + [3] * 40, dtype=np.int32)
+    index, total, classes = ox.plan_placement(labels, lib=lib)
+    assert classes == [(7, 0, 32), (3, 32, 64), (9, 96, 32)] and total == 128
+    assert index[:6].tolist() == [0, 1, 32, 2, 33, 96] and index[6:].tolist() == list(range(34, 74))
+    one, total1, classes1 = ox.plan_placement(np.zeros(65, dtype=np.int32), lib=lib)
+    assert total1 == 96 and classes1 == [(0, 0, 96)] and one.tolist() == list(range(65))
+    out = (ctypes.c_int32 * 4)()
+    assert lib.oalsfx_plan_placement(None, 4, out, None, 0, None) < 0
+    assert lib.oalsfx_plan_placement(out, 0, out, None, 0, None) < 0
+    assert lib.oalsfx_plan_placement(out, 4, out, None, 3, None) < 0   # a capacity without a buffer
