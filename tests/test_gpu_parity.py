@@ -597,6 +597,31 @@ def test_placement_keeps_arbitrary_presets_on_the_class_per_tile_launch(checker)
     assert not y[~used].any()
 
 
+def test_wide_relay_with_send_filters_over_four_seconds(checker):
+    """The 4-slot chain on 5.1 with active send shelf filters (kRelaySfWideHeavy) for 4 s in 2048-frame blocks: every delay
+    line wraps several times, the send filter histories and the six-channel pan gains settle; bit-exact per stream."""
+    lib = _lib()
+    fmt, S, block, nblocks = F.five_point_one, 40, 2048, 94
+    C = ox.channel_count(fmt)
+    slots = [T.equalizer, T.chorus, T.echo, T.eax_reverb]
+    sends = {-1: (0.8, 0.5, 1.0), 0: (0.7, 1.0, 0.4), 2: (1.0, 0.25, 0.5), 3: (0.9, 0.6, 0.8)}
+    total = block * nblocks
+    x = np.stack([H.noise(9000 + s, C, total) for s in range(S)])
+    y = np.empty_like(x)
+    with ox.Engine(S, fmt, 48000, 4, lib=lib) as eng:
+        for i, t in enumerate(slots):
+            eng.set_effect(i, t)
+        eng.set_sends(direct=sends[-1], aux=[sends.get(i, (1.0, 1.0, 1.0)) for i in range(4)])
+        for b in range(nblocks):
+            y[:, b * block:(b + 1) * block] = eng.mix(np.ascontiguousarray(x[:, b * block:(b + 1) * block]))
+        assert eng.launch_count == nblocks and eng.last_kernel == "kRelaySfWideHeavy", (eng.launch_count, eng.last_kernel)
+    script = [("type", i, t) for i, t in enumerate(slots)] + [("send", i, sends.get(i, (1.0, 1.0, 1.0))) for i in range(-1, 4)] + [("apply",)]
+    script += [("mix", block)] * nblocks
+    for s in (0, 31, 39):
+        expect = H.run_script_orc(checker, fmt, 48000, 4, script, x[s])
+        _assert_match(expect, y[s], True, f"stream {s}")
+
+
 def test_waveshaper_divisions_are_ieee_divisions():
     """The distortion stage runs its twelve divisions per sample (oalsfxpp.cpp:4720-4722) as a batched correctly-rounded
     sequence behind one guard instead of through the `/` operator (fx.cuh, FxDistortion::shape).  Bit for bit against
